@@ -1,0 +1,161 @@
+/*
+ * vla_b200.h - C ABI of libvla_b200.so, the sm_100a engine behind VLA-Adapter's predict_action path.
+ *
+ * The reference has no FFI layer: its seam is a set of plain Python method calls
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it replaces.
+ * Signatures carry only plain pointers and sizes (no torch / C++ types).  All device work is
+ * enqueued on the caller-supplied cudaStream_t (passed as void*; NULL = legacy default stream).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative vla_status otherwise; the message is
+ *     available through vla_last_error(engine) (engine functions) or vla_global_error() (ops);
+ *   - the engine is not thread-safe; one engine per device;
+ *   - the caller owns all I/O buffers; the engine owns its (repacked) weights and workspace;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef VLA_B200_H
+#define VLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vla_status {
+  VLA_OK = 0,
+  VLA_ERR_INVALID = -1,      /* bad shape / argument (reference: Python assert / ValueError) */
+  VLA_ERR_DTYPE = -2,        /* unsupported dtype */
+  VLA_ERR_MISSING = -3,      /* a required tensor was never loaded */
+  VLA_ERR_CUDA = -4,         /* CUDA runtime / driver error */
+  VLA_ERR_NOT_FINALIZED = -5 /* vla_predict before vla_finalize */
+} vla_status;
+
+typedef enum vla_dtype { VLA_BF16 = 0, VLA_F32 = 1, VLA_F16 = 2 } vla_dtype;
+
+typedef enum vla_variant {
+  VLA_HEAD_BASE = 0, /* MLPResNetBlock      (prismatic/models/action_heads.py:168) */
+  VLA_HEAD_PRO = 1   /* MLPResNetBlock_Pro  (prismatic/models/action_heads.py:287) */
+} vla_variant;
+
+/*
+ * Engine configuration.  The reference bakes most of these into import-time globals
+ * (prismatic/vla/constants.py:88-91) and the HF config (pretrained_models/configs/config.json);
+ * here they are explicit.  Widths of the three sub-networks are fixed by the architecture
+ * (DINOv2-L/14, SigLIP-so400m/14, Qwen2.5-0.5B, 8x112 policy heads); depths and vocabulary are
+ * configurable so that reduced-depth models can be used in parity tests.
+ */
+typedef struct vla_cfg {
+  int32_t n_images;      /* images per sample (1..3); NUM_PATCHES = 256 * n_images (MP:953) */
+  int32_t chunk_len;     /* NUM_ACTIONS_CHUNK (constants.py:29)  */
+  int32_t action_dim;    /* ACTION_DIM                              */
+  int32_t proprio_dim;   /* PROPRIO_DIM                             */
+  int32_t variant;       /* vla_variant                             */
+  int32_t dino_depth;    /* timm blocks in the DINOv2 tower (24); output taken after block depth-2 */
+  int32_t siglip_depth;  /* timm blocks in the SigLIP tower (27)    */
+  int32_t llm_layers;    /* Qwen2 decoder layers (24; the policy needs exactly 24 taps) */
+  int32_t vocab_size;    /* rows of embed_tokens (151936)           */
+  int32_t max_batch;     /* workspace is sized for this many samples per call */
+  int32_t max_prompt_len;/* and this many prompt tokens (L)         */
+  int32_t causal;        /* 1 = causal LLM attention (stock HF Qwen2), 0 = bidirectional */
+} vla_cfg;
+
+typedef struct vla_engine vla_engine;
+
+/* Replaces: OpenVLAForActionPrediction.__init__ (modeling_prismatic.py:736) + get_action_head /
+ * get_proprio_projector (experiments/robot/openvla_utils.py:482, 412) - allocates an empty engine. */
+int vla_create(const vla_cfg* cfg, vla_engine** out);
+
+/* Replaces: load_state_dict of the three reference modules (openvla_utils.py:230-250, 445, 530).
+ * `name` is the reference state_dict key, prefixed by its module:
+ *   "vla."  + OpenVLAForActionPrediction key   (e.g. vla.vision_backbone.featurizer.blocks.0.attn.qkv.weight)
+ *   "head." + L1RegressionActionHead key       (e.g. head.model.mlp_resnet_blocks.3.q_proj.weight)
+ *   "proprio." + ProprioProjector key          (e.g. proprio.fc1.weight)
+ * `ptr` may be a device or host pointer; the engine copies and repacks, the caller keeps ownership.
+ * Unknown names are rejected with VLA_ERR_INVALID, names the path does not read (e.g. lm_head,
+ * film_gen, attn_pool) are accepted and ignored. */
+int vla_load_tensor(vla_engine* e, const char* name, const void* ptr, int dtype, int ndim,
+                    const int64_t* shape);
+
+/* Replaces: OpenVLAForActionPrediction._unnormalize_actions statistics lookup
+ * (modeling_prismatic.py:786-805, 998-1001).  hi/lo are q99/q01 (BOUNDS_Q99) or max/min (BOUNDS);
+ * mask[i] != 0 means "un-normalise dimension i".  All arrays have action_dim entries (host). */
+int vla_set_action_stats(vla_engine* e, const double* hi, const double* lo, const uint8_t* mask);
+
+/* Checks that every tensor is present, precomputes input-independent constants (the MLPResNet
+ * prologue x0 = ReLU(fc1(LN(0))), action_heads.py:114-116; RoPE tables; tanh(gating_factor)),
+ * allocates the workspace for (max_batch, max_prompt_len). */
+int vla_finalize(vla_engine* e);
+
+/* Replaces: OpenVLAForActionPrediction.predict_action (modeling_prismatic.py:892-972), batched.
+ *   pixel_values : device, bf16, (B, 6*n_images, 224, 224) contiguous   (MP:919)
+ *   ext_ids      : device, int64, (B, L+65) = prompt ids, 64 placeholder ids, STOP   (MP:748-758)
+ *   aq_index     : device, int32, (B, L+65): ActionQuery row to splice at that column or -1
+ *                  (the all_actions_mask / masked_indices of MP:442-452, as indices)
+ *   proprio      : device, fp32, (B, proprio_dim), already normalised (openvla_utils.py:671-701)
+ *   out_norm     : device, fp32, (B, chunk_len, action_dim) normalised actions      (MP:871-872)
+ *   out_unnorm   : device, fp32, (B, chunk_len, action_dim) un-normalised actions   (MP:799-803)
+ *   out_last_ha  : device, bf16, (B, 64, 896) last-layer ActionQuery states or NULL (MP:855, 972)
+ */
+int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
+                const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm,
+                float* out_unnorm, void* out_last_ha, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): the engine stages inputs through its own
+ * pinned buffers, runs vla_predict and copies the results back; synchronises the stream.
+ * This is the end-to-end path bench.py reports as `e2e`. */
+int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
+                     const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm,
+                     float* out_unnorm, void* out_last_ha, void* stream);
+
+/* Debug taps for parity tests: copies an intermediate of the LAST vla_predict call to `dst`
+ * (device or host).  Names: "patches" (B,NP,2176) tower output, "projected" (B,NP,896),
+ * "llm_in" (B,S,896), "hidden.<i>" i in 1..24 (B,S,896) as returned by HF output_hidden_states,
+ * "head_x.<i>" policy state after block i (B,T,896).  Returns the number of bytes through *bytes. */
+int vla_get_tap(vla_engine* e, const char* name, void* dst, size_t capacity, size_t* bytes);
+
+/* Kernel launches issued by this engine's last vla_predict call (own kernels only). */
+long long vla_last_launch_count(const vla_engine* e);
+
+const char* vla_last_error(const vla_engine* e);
+void vla_destroy(vla_engine* e);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator-level entry points (used by the parity tests; each is one of the engine's kernels).
+ * All pointers are device pointers, bf16 unless noted.
+ * ------------------------------------------------------------------------------------------ */
+
+/* C[b,r,n] = epi(sum_k A[b,r,k] W[n,k]) - nn.Linear; see csrc/gemm.cuh for the epilogue.
+ * act: 0 none, 1 GELU(erf), 2 ReLU, 3 SwiGLU (interleaved gate/up rows). */
+int vla_op_gemm(const void* A, long long a_batch_stride, int lda, int rows, int batches,
+                const void* W, int ldw, int N, int K, void* C, long long c_batch_stride, int ldc,
+                const float* bias, const float* colscale, const void* resid,
+                long long r_batch_stride, int ldr, int act, int force_bn, void* stream);
+
+/* y = LayerNorm(x) * w + b over the last dim (nn.LayerNorm, eps given); w, b fp32. */
+int vla_op_layernorm(const void* x, int rows, int dim, int ldx, const float* w, const float* b,
+                     float eps, void* y, int ldy, void* stream);
+
+/* y = x * rsqrt(mean(x^2) + eps) * w (Qwen2RMSNorm); w fp32. */
+int vla_op_rmsnorm(const void* x, int rows, int dim, int ldx, const float* w, float eps, void* y,
+                   int ldy, void* stream);
+
+/* Multi-head attention over a packed qkv buffer.
+ *   q at qkv[row, q_off + h*hd], k at qkv[row, k_off + (h/group)*hd], v likewise; row = b*S + s.
+ *   hd in {64, 72}; causal != 0 applies the lower-triangular mask; scale = hd^-0.5. */
+int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_off, int B, int S,
+                     int n_heads, int group, int hd, int causal, void* out, int ld_out,
+                     void* stream);
+
+/* In-place HF rotate_half RoPE (theta) on `n_heads` heads of width 64 starting at column `off`
+ * of each row; position = row % S. */
+int vla_op_rope(void* x, int ld, int off, int n_heads, int B, int S, float theta, void* stream);
+
+const char* vla_global_error(void);
+long long vla_total_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLA_B200_H */

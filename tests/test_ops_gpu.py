@@ -1,0 +1,180 @@
+"""Operator-level parity: each CUDA kernel (through the C ABI) against a plain PyTorch fp32 reference of
+the same op on the same seeded inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _randn(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+GEMM_SHAPES = [
+    # M, N, K
+    (128, 256, 64),
+    (128, 128, 128),
+    (261, 1024, 1024),     # DINOv2 proj at bs=1 (M tail)
+    (512, 4304, 1152),     # SigLIP fc1 (N tail: 4304 = 16*256 + 208)
+    (512, 1152, 4304),     # SigLIP fc2 (K tail: 4304 = 67*64 + 16)
+    (256, 1024, 592),      # patch embed (K tail)
+    (1250, 1152, 896),     # Qwen qkv, 2 samples
+    (1000, 896, 4864),     # Qwen down
+    (8, 2688, 896),        # policy q/k/v at bs=1 (tiny M)
+    (3000, 8704, 2176),    # projector fc1
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+def test_gemm_plain(M, N, K, bn):
+    from vla_adapter_b200 import ops
+
+    a = _randn(M, K, seed=1)
+    w = _randn(N, K, scale=K ** -0.5, seed=2)
+    out = ops.linear(a, w, force_bn=bn)
+    ref = a.float() @ w.float().T
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 5e-3, (M, N, K, bn)
+    # bf16 rounding of an fp32-accumulated result: elementwise within 1 bf16 ulp of the fp32 reference
+    assert (out.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("act", ["none", "gelu", "relu"])
+def test_gemm_epilogue(act):
+    from vla_adapter_b200 import ops
+
+    M, N, K = 700, 1152, 896
+    a = _randn(M, K, seed=3)
+    w = _randn(N, K, scale=K ** -0.5, seed=4)
+    bias = torch.randn(N, device="cuda")
+    ls = torch.rand(N, device="cuda") + 0.5
+    resid = _randn(M, N, seed=5)
+    out = ops.linear(a, w, bias=bias, act=act, colscale=ls, resid=resid)
+    v = a.float() @ w.float().T + bias
+    if act == "gelu":
+        v = torch.nn.functional.gelu(v)
+    elif act == "relu":
+        v = torch.relu(v)
+    ref = resid.float() + ls * v
+    assert _rel(out, ref) < 5e-3
+    # in-place residual (C aliases resid)
+    x = resid.clone()
+    ops.linear(a, w, bias=bias, act=act, colscale=ls, resid=x, out=x)
+    assert torch.equal(x, out)
+
+
+def test_gemm_swiglu():
+    from vla_adapter_b200 import ops
+
+    M, I, K = 900, 4864, 896
+    a = _randn(M, K, seed=6)
+    wg = _randn(I, K, scale=K ** -0.5, seed=7)
+    wu = _randn(I, K, scale=K ** -0.5, seed=8)
+    # interleave rows in groups of 16: g0..15, u0..15, g16..31, u16..31, ...
+    w = torch.stack([wg.view(I // 16, 16, K), wu.view(I // 16, 16, K)], dim=1).reshape(2 * I, K).contiguous()
+    out = ops.linear(a, w, act="swiglu")
+    ref = torch.nn.functional.silu(a.float() @ wg.float().T) * (a.float() @ wu.float().T)
+    assert out.shape == (M, I)
+    assert _rel(out, ref) < 5e-3
+
+
+def test_gemm_batched_view():
+    from vla_adapter_b200 import ops
+
+    B, R, K, N = 3, 625, 896, 1792
+    a = _randn(B, R, K, seed=9)
+    w = _randn(N, K, scale=K ** -0.5, seed=10)
+    bias = torch.randn(N, device="cuda")
+    out = torch.zeros(B, 600, N, dtype=torch.bfloat16, device="cuda")
+    ops.linear_batched(a, 559, 64, w, out, 3, bias=bias)          # h_a-style slice: rows [559, 623)
+    ref = a[:, 559:623].float() @ w.float().T + bias
+    assert _rel(out[:, 3:67], ref) < 5e-3
+    assert out[:, :3].abs().sum().item() == 0 and out[:, 67:].abs().sum().item() == 0   # nothing else written
+    out.zero_()
+    ops.linear_batched(a, 0, 512, w, out, 65, bias=bias)           # h_t-style slice: rows [0, 512)
+    ref = a[:, :512].float() @ w.float().T + bias
+    assert _rel(out[:, 65:577], ref) < 5e-3
+    assert out[:, :65].abs().sum().item() == 0 and out[:, 577:].abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("dim", [896, 1024, 1152])
+def test_layernorm(dim):
+    from vla_adapter_b200 import ops
+
+    x = _randn(777, dim, seed=11) * 3 + 0.5
+    w = torch.randn(dim, device="cuda")
+    b = torch.randn(dim, device="cuda")
+    y = ops.layernorm(x, w, b, 1e-6)
+    ref = torch.nn.functional.layer_norm(x.float(), (dim,), w, b, 1e-6)
+    assert (y.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+
+
+def test_rmsnorm():
+    from vla_adapter_b200 import ops
+
+    dim = 896
+    x = _randn(1250, dim, seed=12) * 2
+    w = (torch.randn(dim) * 0.1 + 1).to(torch.bfloat16).float().cuda()
+    y = ops.rmsnorm(x, w, 1e-6)
+    xf = x.float()
+    ref = w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(torch.bfloat16).float()
+    assert (y.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+
+
+def _ref_attention(qkv, B, S, H, HKV, hd, causal):
+    q, k, v = qkv.float().split([H * hd, HKV * hd, HKV * hd], dim=-1)
+    q = q.view(B, S, H, hd).transpose(1, 2)
+    k = k.view(B, S, HKV, hd).transpose(1, 2).repeat_interleave(H // HKV, dim=1)
+    v = v.view(B, S, HKV, hd).transpose(1, 2).repeat_interleave(H // HKV, dim=1)
+    s = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    if causal:
+        s = s.masked_fill(torch.ones(S, S, dtype=torch.bool, device=s.device).triu(1), float("-inf"))
+    o = torch.softmax(s, dim=-1) @ v
+    return o.transpose(1, 2).reshape(B * S, H * hd)
+
+
+@pytest.mark.parametrize("B,S,H,HKV,hd,causal", [
+    (2, 261, 16, 16, 64, False),   # DINOv2
+    (2, 256, 16, 16, 72, False),   # SigLIP
+    (2, 625, 14, 2, 64, True),     # Qwen2.5 GQA causal
+    (1, 609, 14, 2, 64, False),    # bidirectional LLM mode
+    (3, 64, 14, 2, 64, True),
+    (1, 1, 16, 16, 72, False),
+])
+def test_attention(B, S, H, HKV, hd, causal):
+    from vla_adapter_b200 import ops
+
+    qkv = _randn(B * S, (H + 2 * HKV) * hd, seed=13)
+    out = ops.attention(qkv, B, S, H, HKV, hd, causal)
+    ref = _ref_attention(qkv, B, S, H, HKV, hd, causal)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 2e-2
+    assert _rel(out, ref) < 1e-2
+
+
+def test_rope():
+    from vla_adapter_b200 import ops
+
+    B, S, H, HKV, hd, theta = 2, 625, 14, 2, 64, 1e6
+    x = _randn(B * S, (H + 2 * HKV) * hd, seed=14)
+    y = x.clone()
+    ops.rope_(y, 0, H + HKV, B, S, theta)
+    inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    ang = torch.arange(S).float()[:, None] * inv[None, :]
+    emb = torch.cat([ang, ang], -1)
+    cos, sin = emb.cos().to(torch.bfloat16).cuda(), emb.sin().to(torch.bfloat16).cuda()
+    xv = x[:, : (H + HKV) * hd].view(B, S, H + HKV, hd)
+    rot = torch.cat([-xv[..., hd // 2:], xv[..., : hd // 2]], -1)
+    ref = xv * cos[None, :, None, :] + rot * sin[None, :, None, :]      # bf16 eager arithmetic, like HF
+    got = y[:, : (H + HKV) * hd].view(B, S, H + HKV, hd)
+    assert (got.float() - ref.float()).abs().max().item() <= 0.0625     # rare 1-ulp table flips only
+    assert (got.float() - ref.float()).abs().mean().item() < 1e-3
+    assert torch.equal(y[:, (H + HKV) * hd:], x[:, (H + HKV) * hd:])     # v untouched

@@ -1,0 +1,84 @@
+// extern "C" operator-level entry points declared in include/vla_b200.h (parity-test surface).
+#include "../../include/vla_b200.h"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+#include <string>
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const char* msg) {
+  g_err = msg ? msg : "unknown error";
+  return code;
+}
+}  // namespace
+
+extern "C" {
+
+const char* vla_global_error(void) { return g_err.c_str(); }
+
+long long vla_total_launch_count(void) { return vla::gemm_launch_count() + vla::ops_launch_count(); }
+
+int vla_op_gemm(const void* A, long long a_batch_stride, int lda, int rows, int batches, const void* W,
+                int ldw, int N, int K, void* C, long long c_batch_stride, int ldc, const float* bias,
+                const float* colscale, const void* resid, long long r_batch_stride, int ldr, int act,
+                int force_bn, void* stream) {
+  vla::GemmArgs g;
+  g.A = static_cast<const __nv_bfloat16*>(A);
+  g.a_batch_stride = a_batch_stride;
+  g.lda = lda;
+  g.rows = rows;
+  g.batches = batches;
+  g.W = static_cast<const __nv_bfloat16*>(W);
+  g.ldw = ldw;
+  g.N = N;
+  g.K = K;
+  g.C = static_cast<__nv_bfloat16*>(C);
+  g.c_batch_stride = c_batch_stride;
+  g.ldc = ldc;
+  g.bias = bias;
+  g.colscale = colscale;
+  g.resid = static_cast<const __nv_bfloat16*>(resid);
+  g.r_batch_stride = r_batch_stride;
+  g.ldr = ldr;
+  g.act = act;
+  g.force_bn = force_bn;
+  const char* err = nullptr;
+  int rc = vla::gemm_launch(g, static_cast<cudaStream_t>(stream), &err);
+  if (rc) return fail(rc, err);
+  return 0;
+}
+
+int vla_op_layernorm(const void* x, int rows, int dim, int ldx, const float* w, const float* b, float eps,
+                     void* y, int ldy, void* stream) {
+  const char* err = nullptr;
+  int rc = vla::layernorm_launch(static_cast<const __nv_bfloat16*>(x), rows, dim, ldx, w, b, eps,
+                                 static_cast<__nv_bfloat16*>(y), ldy, static_cast<cudaStream_t>(stream), &err);
+  return rc ? fail(rc, err) : 0;
+}
+
+int vla_op_rmsnorm(const void* x, int rows, int dim, int ldx, const float* w, float eps, void* y, int ldy,
+                   void* stream) {
+  const char* err = nullptr;
+  int rc = vla::rmsnorm_launch(static_cast<const __nv_bfloat16*>(x), rows, dim, ldx, w, eps,
+                               static_cast<__nv_bfloat16*>(y), ldy, static_cast<cudaStream_t>(stream), &err);
+  return rc ? fail(rc, err) : 0;
+}
+
+int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_off, int B, int S, int n_heads,
+                     int group, int hd, int causal, void* out, int ld_out, void* stream) {
+  const char* err = nullptr;
+  int rc = vla::attention_launch(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, q_off, k_off, v_off, B, S,
+                                 n_heads, group, hd, causal, static_cast<__nv_bfloat16*>(out), ld_out,
+                                 static_cast<cudaStream_t>(stream), &err);
+  return rc ? fail(rc, err) : 0;
+}
+
+int vla_op_rope(void* x, int ld, int off, int n_heads, int B, int S, float theta, void* stream) {
+  const char* err = nullptr;
+  int rc = vla::rope_launch(static_cast<__nv_bfloat16*>(x), ld, off, n_heads, B, S, theta,
+                            static_cast<cudaStream_t>(stream), &err);
+  return rc ? fail(rc, err) : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// Host-side interface of the tcgen05 GEMM (see gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace vla {
+
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SWIGLU = 3 };
+
+// C[b, r, n] = epi( sum_k A[b, r, k] * W[n, k] )      (nn.Linear convention: W is [N, K], K contiguous)
+//
+// A and C are 3-D *views*: `batches` slabs of `rows` rows each, slab b starting at
+// A + b * a_batch_stride (elements).  This is how the engine reads "rows [r0, r0+rows) of every
+// sample" of a hidden state (reference slices at modeling_prismatic.py:855,858) and how it writes
+// patch rows behind the prefix tokens / into the LLM input buffer without gather copies.
+//
+// Epilogue (fp32): v = acc + bias[n]; v = act(v); v = colscale[n] * v; v += resid[b, r, n]; C = bf16(v)
+// ACT_SWIGLU: W rows are interleaved in groups of 16 (g0..15, u0..15, g16.., u16..); the epilogue
+// writes silu(g) * u to column n/2 (bias/colscale/resid are not applied in this mode).
+struct GemmArgs {
+  const __nv_bfloat16* A = nullptr;
+  long long a_batch_stride = 0;  // elements
+  int lda = 0;                   // elements, multiple of 8
+  int rows = 0;                  // rows per batch slab
+  int batches = 1;
+  const __nv_bfloat16* W = nullptr;
+  int ldw = 0;  // elements, multiple of 8
+  int N = 0;    // multiple of 8
+  int K = 0;    // logical K (TMA zero-fills the tail of the last 64-wide K block)
+  __nv_bfloat16* C = nullptr;
+  long long c_batch_stride = 0;
+  int ldc = 0;
+  const float* bias = nullptr;      // [N] fp32
+  const float* colscale = nullptr;  // [N] fp32 (LayerScale)
+  const __nv_bfloat16* resid = nullptr;
+  long long r_batch_stride = 0;
+  int ldr = 0;
+  int act = ACT_NONE;
+  int force_bn = 0;  // 0 = heuristic, else 64/128/256
+};
+
+// Returns 0 on success, negative on error (message in *err if non-null).
+int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err);
+
+// Number of GEMM kernel launches issued since process start (for bench.py's gpu_launches).
+long long gemm_launch_count();
+
+}  // namespace vla

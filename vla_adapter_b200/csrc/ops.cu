@@ -1,0 +1,394 @@
+// Bandwidth-bound kernels of the predict_action path: norms, RoPE, im2col, token assembly,
+// skinny linears.  All are vectorised (16-byte) and coalesced; reductions use warp shuffles.
+#include "common.cuh"
+#include "ops.cuh"
+
+#include <atomic>
+
+namespace vla {
+
+namespace {
+std::atomic<long long> g_ops_launches{0};
+
+inline int check_launch(const char** err) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = cudaGetErrorString(e);
+    return -4;
+  }
+  g_ops_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+constexpr int MAX_VEC_PER_LANE = 5;  // dim <= 5*32*8 = 1280
+
+// ------------------------------------------------------------------ LayerNorm / RMSNorm
+// One warp per row.  The row is read once into registers (16-byte loads), statistics in fp32.
+template <bool RMS>
+__global__ void __launch_bounds__(256)
+norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long long x_bs, int dim, int ldx,
+            const float* __restrict__ w, const float* __restrict__ b, float eps,
+            __nv_bfloat16* __restrict__ y, long long y_bs, int ldy) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(rows) * batches;
+  if (warp >= total) return;
+  const int bi = warp / rows;
+  const int r = warp - bi * rows;
+  const __nv_bfloat16* xr = x + bi * x_bs + static_cast<long long>(r) * ldx;
+  __nv_bfloat16* yr = y + bi * y_bs + static_cast<long long>(r) * ldy;
+  const int nvec = dim >> 3;
+
+  float v[MAX_VEC_PER_LANE][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+      v[i][0] = a0.x; v[i][1] = a0.y; v[i][2] = a1.x; v[i][3] = a1.y;
+      v[i][4] = a2.x; v[i][5] = a2.y; v[i][6] = a3.x; v[i][7] = a3.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += RMS ? v[i][j] * v[i][j] : v[i][j];
+    }
+  }
+  sum = warp_sum(sum);
+  float mean = 0.f, rstd;
+  if (RMS) {
+    rstd = rsqrtf(sum / dim + eps);
+  } else {
+    mean = sum / dim;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          var += d * d;
+        }
+      }
+    }
+    var = warp_sum(var);
+    rstd = rsqrtf(var / dim + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + vi * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + vi * 8 + 4));
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float o[8];
+      if (RMS) {
+        // HF: weight * (x_fp32 * rsqrt(var + eps)).to(bf16)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = ww[j] * bf16_round(v[i][j] * rstd);
+      } else {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + vi * 8 + 4));
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * ww[j] + bb[j];
+      }
+      *reinterpret_cast<uint4*>(yr + vi * 8) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                                          pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ RoPE (HF Qwen2, rotate_half)
+__global__ void rope_table_kernel(float* cos_t, float* sin_t, int S, int half, float theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * half) return;
+  const int pos = i / half, j = i - pos * half;
+  // transformers Qwen2RotaryEmbedding: inv_freq fp32, angle = pos * inv_freq in fp32, cos/sin -> bf16
+  const float inv_freq = static_cast<float>(1.0 / pow(static_cast<double>(theta), (2.0 * j) / (2.0 * half)));
+  const float ang = static_cast<float>(pos) * inv_freq;
+  cos_t[i] = bf16_round(static_cast<float>(cos(static_cast<double>(ang))));
+  sin_t[i] = bf16_round(static_cast<float>(sin(static_cast<double>(ang))));
+}
+
+// One thread handles 8 contiguous dims j..j+7 (j < 32) of one head and their partners j+32.
+__global__ void __launch_bounds__(256)
+rope_apply_kernel(__nv_bfloat16* __restrict__ x, int ld, int off, int n_heads, long long rows, int S,
+                  const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = rows * n_heads * 4;
+  if (idx >= total) return;
+  const int part = static_cast<int>(idx & 3);
+  const long long t = idx >> 2;
+  const int h = static_cast<int>(t % n_heads);
+  const long long row = t / n_heads;
+  const int pos = static_cast<int>(row % S);
+  __nv_bfloat16* p = x + row * ld + off + h * 64 + part * 8;
+  const uint4 lo = *reinterpret_cast<const uint4*>(p);
+  const uint4 hi = *reinterpret_cast<const uint4*>(p + 32);
+  const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+  float a[8], bq[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16(lw[i]), g = unpack_bf16(hw[i]);
+    a[2 * i] = f.x; a[2 * i + 1] = f.y; bq[2 * i] = g.x; bq[2 * i + 1] = g.y;
+  }
+  const float* c = cos_t + pos * 32 + part * 8;
+  const float* s = sin_t + pos * 32 + part * 8;
+  float o1[8], o2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float cs = c[i], sn = s[i];
+    // q_embed = (q * cos) + (rotate_half(q) * sin), each op rounded to bf16 like the eager reference
+    o1[i] = bf16_round(bf16_round(a[i] * cs) + bf16_round(-bq[i] * sn));
+    o2[i] = bf16_round(bf16_round(bq[i] * cs) + bf16_round(a[i] * sn));
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(o1[0], o1[1]), pack_bf16(o1[2], o1[3]),
+                                            pack_bf16(o1[4], o1[5]), pack_bf16(o1[6], o1[7]));
+  *reinterpret_cast<uint4*>(p + 32) = make_uint4(pack_bf16(o2[0], o2[1]), pack_bf16(o2[2], o2[3]),
+                                                 pack_bf16(o2[4], o2[5]), pack_bf16(o2[6], o2[7]));
+}
+
+// ------------------------------------------------------------------ im2col for the 14x14/14 patch conv
+// One thread per (patch row vector of 14 pixels): reads 14 contiguous bf16 (28 B) of the image, writes
+// them at k = c*196 + ky*14 + [0,14).  Grid: (image slab, patch) x (c, ky).
+__global__ void __launch_bounds__(256)
+im2col_kernel(const __nv_bfloat16* __restrict__ pix, int n_img, int tower, long long n_slabs,
+              __nv_bfloat16* __restrict__ out) {
+  constexpr int KP = 592;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = n_slabs * 256 * 43;  // 42 (c,ky) segments + 1 zero-pad segment
+  if (idx >= total) return;
+  const int seg = static_cast<int>(idx % 43);
+  const long long pr = idx / 43;  // slab*256 + patch
+  const int patch = static_cast<int>(pr & 255);
+  const long long slab = pr >> 8;
+  __nv_bfloat16* orow = out + pr * KP;
+  if (seg == 42) {
+    *reinterpret_cast<uint2*>(orow + 588) = make_uint2(0u, 0u);
+    return;
+  }
+  const int c = seg / 14, ky = seg - c * 14;
+  const int py = patch >> 4, px = patch & 15;
+  const long long b = slab / n_img;
+  const int img = static_cast<int>(slab - b * n_img);
+  const int ch = img * 6 + tower * 3 + c;
+  const __nv_bfloat16* src =
+      pix + ((b * (6 * n_img) + ch) * 224 + (py * 14 + ky)) * 224LL + px * 14;  // 4-byte aligned
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(orow + c * 196 + ky * 14);  // 4-byte aligned
+#pragma unroll
+  for (int i = 0; i < 7; ++i) d32[i] = __ldg(s32 + i);
+}
+
+__global__ void prefix_tokens_kernel(__nv_bfloat16* __restrict__ x, int n_slabs, long long slab_stride,
+                                     int dim, const __nv_bfloat16* __restrict__ prefix, int n_prefix) {
+  const int nvec = dim >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n_slabs) * n_prefix * nvec;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % nvec);
+  const long long t = idx / nvec;
+  const int r = static_cast<int>(t % n_prefix);
+  const long long slab = t / n_prefix;
+  const uint4 val = __ldg(reinterpret_cast<const uint4*>(prefix + static_cast<long long>(r) * dim + v * 8));
+  *reinterpret_cast<uint4*>(x + slab * slab_stride + static_cast<long long>(r) * dim + v * 8) = val;
+}
+
+// ------------------------------------------------------------------ LLM input assembly
+__global__ void __launch_bounds__(128)
+assemble_kernel(__nv_bfloat16* __restrict__ x, int B, int S, int NP, int Lext, int dim,
+                const int64_t* __restrict__ ext_ids, const int32_t* __restrict__ aq_index,
+                const __nv_bfloat16* __restrict__ embed, int vocab, const __nv_bfloat16* __restrict__ aq_table,
+                int n_aq, int* err_flag) {
+  // one block per (sample, text column j in [0, Lext))
+  const int j = blockIdx.x % Lext;
+  const int b = blockIdx.x / Lext;
+  const int s = (j == 0) ? 0 : NP + j;
+  const int aq = aq_index[static_cast<long long>(b) * Lext + j];
+  const __nv_bfloat16* src;
+  if (aq >= 0) {
+    if (aq >= n_aq) {
+      if (threadIdx.x == 0) atomicExch(err_flag, 2);
+      return;
+    }
+    src = aq_table + static_cast<long long>(aq) * dim;
+  } else {
+    const int64_t id = ext_ids[static_cast<long long>(b) * Lext + j];
+    if (id < 0 || id >= vocab) {
+      if (threadIdx.x == 0) atomicExch(err_flag, 1);
+      return;
+    }
+    src = embed + id * dim;
+  }
+  __nv_bfloat16* dst = x + (static_cast<long long>(b) * S + s) * dim;
+  for (int v = threadIdx.x; v < (dim >> 3); v += blockDim.x)
+    reinterpret_cast<uint4*>(dst)[v] = __ldg(reinterpret_cast<const uint4*>(src) + v);
+}
+
+// ------------------------------------------------------------------ skinny linear
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const void* __restrict__ x, int x_is_f32, int ldx, int M, int K,
+                     const __nv_bfloat16* __restrict__ W, int ldw, int N, const float* __restrict__ bias,
+                     int act, __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ out_f32) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= static_cast<long long>(M) * N) return;
+  const int n = static_cast<int>(warp % N);
+  const int m = static_cast<int>(warp / N);
+  const __nv_bfloat16* wr = W + static_cast<long long>(n) * ldw;
+  float acc = 0.f;
+  if (x_is_f32) {
+    const float* xr = static_cast<const float*>(x) + static_cast<long long>(m) * ldx;
+    for (int k = lane; k < K; k += 32) acc += bf16_round(xr[k]) * __bfloat162float(wr[k]);
+  } else {
+    const __nv_bfloat16* xr = static_cast<const __nv_bfloat16*>(x) + static_cast<long long>(m) * ldx;
+    if ((K & 7) == 0 && (ldx & 7) == 0 && (ldw & 7) == 0) {
+      for (int v = lane; v < (K >> 3); v += 32) {
+        const uint4 a = *reinterpret_cast<const uint4*>(xr + v * 8);
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(wr + v * 8));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 fa = unpack_bf16(aw[i]), fw = unpack_bf16(ww[i]);
+          acc += fa.x * fw.x + fa.y * fw.y;
+        }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) acc += __bfloat162float(xr[k]) * __bfloat162float(wr[k]);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (bias) acc += bias[n];
+    if (act == 1) acc = gelu_erf(acc);
+    else if (act == 2) acc = fmaxf(acc, 0.f);
+    const __nv_bfloat16 o = __float2bfloat16_rn(acc);
+    if (out) out[static_cast<long long>(m) * ldo + n] = o;
+    if (out_f32) out_f32[static_cast<long long>(m) * N + n] = __bfloat162float(o);
+  }
+}
+
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long src_bs, int ld, int r0,
+                                   int rows, int batches, int dim, __nv_bfloat16* __restrict__ dst) {
+  const int nvec = dim >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(batches) * rows * nvec;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % nvec);
+  const long long t = idx / nvec;
+  const int r = static_cast<int>(t % rows);
+  const long long b = t / rows;
+  reinterpret_cast<uint4*>(dst)[idx] =
+      *reinterpret_cast<const uint4*>(src + b * src_bs + static_cast<long long>(r0 + r) * ld + v * 8);
+}
+
+}  // namespace
+
+long long ops_launch_count() { return g_ops_launches.load(); }
+void ops_count_launch(int n) { g_ops_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int layernorm_launch_3d(const __nv_bfloat16* x, int rows, int batches, long long x_bs, int dim, int ldx,
+                        const float* w, const float* b, float eps, __nv_bfloat16* y, long long y_bs, int ldy,
+                        cudaStream_t s, const char** err) {
+  if ((dim & 7) || dim > MAX_VEC_PER_LANE * 256 || (ldx & 7) || (ldy & 7)) {
+    if (err) *err = "layernorm: dim must be a multiple of 8 and <= 1280";
+    return -1;
+  }
+  const long long total = static_cast<long long>(rows) * batches;
+  const int blocks = static_cast<int>((total + 7) / 8);
+  norm_kernel<false><<<blocks, 256, 0, s>>>(x, rows, batches, x_bs, dim, ldx, w, b, eps, y, y_bs, ldy);
+  return check_launch(err);
+}
+
+int layernorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const float* w, const float* b,
+                     float eps, __nv_bfloat16* y, int ldy, cudaStream_t s, const char** err) {
+  return layernorm_launch_3d(x, rows, 1, 0, dim, ldx, w, b, eps, y, 0, ldy, s, err);
+}
+
+int rmsnorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const float* w, float eps,
+                   __nv_bfloat16* y, int ldy, cudaStream_t s, const char** err) {
+  if ((dim & 7) || dim > MAX_VEC_PER_LANE * 256 || (ldx & 7) || (ldy & 7)) {
+    if (err) *err = "rmsnorm: dim must be a multiple of 8 and <= 1280";
+    return -1;
+  }
+  const int blocks = (rows + 7) / 8;
+  norm_kernel<true><<<blocks, 256, 0, s>>>(x, rows, 1, 0, dim, ldx, w, nullptr, eps, y, 0, ldy);
+  return check_launch(err);
+}
+
+int rope_table_launch(float* cos_t, float* sin_t, int S, int half, float theta, cudaStream_t s,
+                      const char** err) {
+  const int total = S * half;
+  rope_table_kernel<<<(total + 255) / 256, 256, 0, s>>>(cos_t, sin_t, S, half, theta);
+  return check_launch(err);
+}
+
+int rope_apply_launch(__nv_bfloat16* x, int ld, int off, int n_heads, int B, int S, const float* cos_t,
+                      const float* sin_t, cudaStream_t s, const char** err) {
+  if ((ld & 7) || (off & 7)) {
+    if (err) *err = "rope: ld/off must be multiples of 8";
+    return -1;
+  }
+  const long long rows = static_cast<long long>(B) * S;
+  const long long total = rows * n_heads * 4;
+  rope_apply_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(x, ld, off, n_heads, rows, S, cos_t,
+                                                                          sin_t);
+  return check_launch(err);
+}
+
+int rope_launch(__nv_bfloat16* x, int ld, int off, int n_heads, int B, int S, float theta, cudaStream_t s,
+                const char** err) {
+  float* tab = nullptr;
+  if (cudaMallocAsync(&tab, sizeof(float) * 2 * S * 32, s) != cudaSuccess) {
+    if (err) *err = "rope: cudaMallocAsync failed";
+    return -4;
+  }
+  int rc = rope_table_launch(tab, tab + S * 32, S, 32, theta, s, err);
+  if (!rc) rc = rope_apply_launch(x, ld, off, n_heads, B, S, tab, tab + S * 32, s, err);
+  cudaFreeAsync(tab, s);
+  return rc;
+}
+
+int im2col_launch(const __nv_bfloat16* pix, int B, int n_img, int tower, __nv_bfloat16* out, cudaStream_t s,
+                  const char** err) {
+  const long long n_slabs = static_cast<long long>(B) * n_img;
+  const long long total = n_slabs * 256 * 43;
+  im2col_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(pix, n_img, tower, n_slabs, out);
+  return check_launch(err);
+}
+
+int prefix_tokens_launch(__nv_bfloat16* x, int n_slabs, long long slab_stride, int dim,
+                         const __nv_bfloat16* prefix, int n_prefix, cudaStream_t s, const char** err) {
+  const long long total = static_cast<long long>(n_slabs) * n_prefix * (dim >> 3);
+  prefix_tokens_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(x, n_slabs, slab_stride, dim,
+                                                                            prefix, n_prefix);
+  return check_launch(err);
+}
+
+int assemble_launch(__nv_bfloat16* x, int B, int S, int NP, int Lext, int dim, const int64_t* ext_ids,
+                    const int32_t* aq_index, const __nv_bfloat16* embed, int vocab,
+                    const __nv_bfloat16* aq_table, int n_aq, int* err_flag, cudaStream_t s, const char** err) {
+  assemble_kernel<<<B * Lext, 128, 0, s>>>(x, B, S, NP, Lext, dim, ext_ids, aq_index, embed, vocab, aq_table,
+                                           n_aq, err_flag);
+  return check_launch(err);
+}
+
+int skinny_linear_launch(const void* x, int x_is_f32, int ldx, int M, int K, const __nv_bfloat16* W, int ldw,
+                         int N, const float* bias, int act, __nv_bfloat16* out, int ldo, float* out_f32,
+                         cudaStream_t s, const char** err) {
+  const long long warps = static_cast<long long>(M) * N;
+  skinny_linear_kernel<<<static_cast<int>((warps + 7) / 8), 256, 0, s>>>(x, x_is_f32, ldx, M, K, W, ldw, N,
+                                                                        bias, act, out, ldo, out_f32);
+  return check_launch(err);
+}
+
+int gather_rows_launch(const __nv_bfloat16* src, long long src_bs, int ld, int r0, int rows, int batches,
+                       int dim, __nv_bfloat16* dst, cudaStream_t s, const char** err) {
+  const long long total = static_cast<long long>(batches) * rows * (dim >> 3);
+  gather_rows_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(src, src_bs, ld, r0, rows, batches,
+                                                                          dim, dst);
+  return check_launch(err);
+}
+
+}  // namespace vla

@@ -1,0 +1,93 @@
+// Host-side launchers of the bandwidth-bound / small kernels (ops.cu, attention.cu, policy.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace vla {
+
+long long ops_launch_count();
+void ops_count_launch(int n = 1);
+
+// nn.LayerNorm over the last dim; one warp per row, fp32 statistics, bf16 in/out.
+int layernorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const float* w, const float* b,
+                     float eps, __nv_bfloat16* y, int ldy, cudaStream_t s, const char** err);
+// Same, for a 3-D row view (batch slabs), used to normalise "rows [r0, r0+rows) of every image".
+int layernorm_launch_3d(const __nv_bfloat16* x, int rows, int batches, long long x_bs, int dim, int ldx,
+                        const float* w, const float* b, float eps, __nv_bfloat16* y, long long y_bs, int ldy,
+                        cudaStream_t s, const char** err);
+
+// Qwen2RMSNorm (transformers Qwen2RMSNorm.forward): bf16(x * rsqrt(mean x^2 + eps)) * w.
+int rmsnorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const float* w, float eps,
+                   __nv_bfloat16* y, int ldy, cudaStream_t s, const char** err);
+
+// cos/sin tables (fp32 values already rounded to bf16), [S][half] each; inv_freq_j = theta^(-2j/(2*half)).
+int rope_table_launch(float* cos_t, float* sin_t, int S, int half, float theta, cudaStream_t s,
+                      const char** err);
+// HF rotate_half RoPE, in place, width-64 heads: out = bf16(bf16(x*cos) + bf16(rot(x)*sin)).
+int rope_apply_launch(__nv_bfloat16* x, int ld, int off, int n_heads, int B, int S, const float* cos_t,
+                      const float* sin_t, cudaStream_t s, const char** err);
+int rope_launch(__nv_bfloat16* x, int ld, int off, int n_heads, int B, int S, float theta, cudaStream_t s,
+                const char** err);
+
+// Flash attention (attention.cu). hd in {64, 72}.
+int attention_launch(const __nv_bfloat16* qkv, int ld_qkv, int q_off, int k_off, int v_off, int B, int S,
+                     int n_heads, int group, int hd, int causal, __nv_bfloat16* out, int ld_out,
+                     cudaStream_t s, const char** err);
+
+// Patch-embed im2col: pixel_values (B, 6*n_img, 224, 224) bf16 -> A[(b*n_img+i)*256 + p, 592]
+// with k = c*196 + ky*14 + kx (Conv2d weight order), columns 588..591 zero.  tower 0 reads channels
+// [6i, 6i+3) (DINOv2), tower 1 reads [6i+3, 6i+6) (SigLIP)  (modeling_prismatic.py:220-230).
+int im2col_launch(const __nv_bfloat16* pix, int B, int n_img, int tower, __nv_bfloat16* out, cudaStream_t s,
+                  const char** err);
+
+// Writes the DINOv2 prefix rows (cls + 4 register tokens, no pos-embed) of every image slab.
+int prefix_tokens_launch(__nv_bfloat16* x, int n_slabs, long long slab_stride, int dim,
+                         const __nv_bfloat16* prefix /*[5, dim]*/, int n_prefix, cudaStream_t s,
+                         const char** err);
+
+// LLM input assembly (modeling_prismatic.py:418-454, 500-502): for sequence position s of sample b
+//   s == 0           -> embed[ext_ids[b,0]]
+//   1 <= s <= NP     -> left untouched (projector output is written there by the GEMM epilogue)
+//   s > NP, j = s-NP -> aq_index[b,j] >= 0 ? action_queries[aq_index[b,j]] : embed[ext_ids[b,j]]
+int assemble_launch(__nv_bfloat16* x, int B, int S, int NP, int Lext, int dim, const int64_t* ext_ids,
+                    const int32_t* aq_index, const __nv_bfloat16* embed, int vocab,
+                    const __nv_bfloat16* aq_table, int n_aq, int* err_flag, cudaStream_t s, const char** err);
+
+// out[m, n] = act(sum_k x[m,k] W[n,k] + b[n]) for skinny problems (tiny M or N); one warp per output.
+// x may be fp32 (x_is_f32) - it is rounded to bf16 first (reference casts proprio to bf16, AH:53).
+// out_f32 != null additionally receives the bf16-rounded value as fp32.
+int skinny_linear_launch(const void* x, int x_is_f32, int ldx, int M, int K, const __nv_bfloat16* W, int ldw,
+                         int N, const float* bias, int act, __nv_bfloat16* out, int ldo, float* out_f32,
+                         cudaStream_t s, const char** err);
+
+// Bridge-Attention core (policy.cu); see policy.cu for the layout.
+struct PolicyAttnArgs {
+  const __nv_bfloat16* qkv_self;  // [B*T, 3*896]: q | k_self | v_self of the current x
+  const __nv_bfloat16* kv_a;      // [B, 64, 1792]  K|V of the ActionQuery rows (h_a)
+  const __nv_bfloat16* kv_p;      // [B, 1792] (+ row stride ld_p) K|V of the proprio row
+  int ld_p;
+  const __nv_bfloat16* kv_t;      // [B, NP, 1792] K|V of the task rows (h_t)
+  int B, T, NP;
+  float gate;                     // tanh(gating_factor)
+  int pro;                        // 0: base (gate on h_t segment, no RoPE); 1: Pro (RoPE, gate on h_t)
+  const float* rope_cos;          // [max_pos, 112] (Pro only; bf16-rounded fp32)
+  const float* rope_sin;
+  __nv_bfloat16* out;             // [B*T, 896]
+};
+int policy_attention_launch(const PolicyAttnArgs& a, cudaStream_t s, const char** err);
+
+// Final regression epilogue: out_norm[b,t,a] = fc2(LN(x)) ; out_unnorm = where(mask, 0.5*(a+1)*(hi-lo+1e-8)+lo, a)
+int head_out_launch(const __nv_bfloat16* x, int rows, const float* ln_w, const float* ln_b,
+                    const __nv_bfloat16* W /*[A, 896]*/, const float* bias, int A, const float* hi,
+                    const float* lo, const uint8_t* mask, float* out_norm, float* out_unnorm, cudaStream_t s,
+                    const char** err);
+
+// Pro-variant RoPE table (action_heads.py:150-164): angle(t, j) = t * inv_freq[j mod 56], hd = 112.
+int policy_rope_table_launch(float* cos_t, float* sin_t, int max_pos, cudaStream_t s, const char** err);
+
+// Copies rows [r0, r0+rows) of every slab into a dense buffer (tap extraction).
+int gather_rows_launch(const __nv_bfloat16* src, long long src_bs, int ld, int r0, int rows, int batches,
+                       int dim, __nv_bfloat16* dst, cudaStream_t s, const char** err);
+
+}  // namespace vla

@@ -1,0 +1,93 @@
+"""Thin torch-tensor wrappers over the operator-level C-ABI entry points (vla_op_*).  Torch is only the
+owner of device memory and of the current stream; all arithmetic happens in libvla_b200.so."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+ACT = {"none": 0, "gelu": 1, "relu": 2, "swiglu": 3}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vla_adapter_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias=None, act="none", colscale=None, resid=None, out=None,
+           force_bn: int = 0) -> torch.Tensor:
+    """out = epi(a @ w.T). a: (M, K) bf16 (row stride may exceed K), w: (N, K) bf16, bias/colscale fp32."""
+    _need_cuda(a, w, bias, colscale, resid, out)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if act == "swiglu" else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.bfloat16, device=a.device)
+    lib = _lib.load()
+    rc = lib.vla_op_gemm(_ptr(a), 0, a.stride(0), M, 1, _ptr(w), w.stride(0), N, K, _ptr(out), 0, out.stride(0),
+                         _ptr(bias), _ptr(colscale), _ptr(resid), 0, resid.stride(0) if resid is not None else 0,
+                         ACT[act], force_bn, _stream())
+    _lib.check(rc)
+    return out
+
+
+def linear_batched(a: torch.Tensor, row0: int, rows: int, w: torch.Tensor, out: torch.Tensor, out_row0: int,
+                   bias=None, act="none") -> torch.Tensor:
+    """3-D view form: a is (B, R, K); reads rows [row0, row0+rows) of every slab, writes rows
+    [out_row0, out_row0+rows) of every slab of out (B, R2, N)."""
+    _need_cuda(a, w, out)
+    B, R, K = a.shape
+    N = w.shape[0]
+    lib = _lib.load()
+    a_v = a[:, row0:, :]
+    o_v = out[:, out_row0:, :]
+    rc = lib.vla_op_gemm(a_v.data_ptr(), a.stride(0), a.stride(1), rows, B, _ptr(w), w.stride(0), N, K,
+                         o_v.data_ptr(), out.stride(0), out.stride(1), _ptr(bias), None, None, 0, 0, ACT[act], 0,
+                         _stream())
+    _lib.check(rc)
+    return out
+
+
+def layernorm(x, w, b, eps=1e-6):
+    _need_cuda(x, w, b)
+    y = torch.empty_like(x)
+    rows, dim = x.shape
+    _lib.check(_lib.load().vla_op_layernorm(_ptr(x), rows, dim, x.stride(0), _ptr(w), _ptr(b), eps, _ptr(y),
+                                             y.stride(0), _stream()))
+    return y
+
+
+def rmsnorm(x, w, eps=1e-6):
+    _need_cuda(x, w)
+    y = torch.empty_like(x)
+    rows, dim = x.shape
+    _lib.check(_lib.load().vla_op_rmsnorm(_ptr(x), rows, dim, x.stride(0), _ptr(w), eps, _ptr(y), y.stride(0),
+                                           _stream()))
+    return y
+
+
+def attention(qkv, B, S, n_heads, n_kv_heads, hd, causal):
+    """qkv: (B*S, (n_heads + 2*n_kv_heads) * hd) packed [q | k | v]."""
+    _need_cuda(qkv)
+    out = torch.empty((B * S, n_heads * hd), dtype=torch.bfloat16, device=qkv.device)
+    q_off, k_off, v_off = 0, n_heads * hd, (n_heads + n_kv_heads) * hd
+    _lib.check(_lib.load().vla_op_attention(_ptr(qkv), qkv.stride(0), q_off, k_off, v_off, B, S, n_heads,
+                                             n_heads // n_kv_heads, hd, int(causal), _ptr(out), out.stride(0),
+                                             _stream()))
+    return out
+
+
+def rope_(x, off, n_heads, B, S, theta):
+    _need_cuda(x)
+    _lib.check(_lib.load().vla_op_rope(_ptr(x), x.stride(0), off, n_heads, B, S, float(theta), _stream()))
+    return x
