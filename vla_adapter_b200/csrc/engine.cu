@@ -1,0 +1,796 @@
+// The engine behind include/vla_b200.h: weight intake/repacking, workspace, and the batched
+// predict_action forward (vision towers -> projector -> Qwen2.5 prefill with per-layer taps ->
+// Bridge-Attention policy -> un-normalised action chunks) as one stream of own kernels.
+//
+// Reference call stack being replaced: OpenVLAForActionPrediction.predict_action
+// (prismatic/extern/hf/modeling_prismatic.py:892-972) -> _process_vision_features (:463) ->
+// _regression_or_discrete_prediction (:808-889) -> L1RegressionActionHead.predict_action
+// (prismatic/models/action_heads.py:43-81) -> _unnormalize_actions (:786-805).
+#include "../../include/vla_b200.h"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using bf16 = __nv_bfloat16;
+
+namespace {
+
+constexpr int D_DINO = 1024, F_DINO = 4096, TOK_DINO = 261, PRE_DINO = 5;
+constexpr int D_SIG = 1152, F_SIG = 4304, TOK_SIG = 256;
+constexpr int D_VIS = D_DINO + D_SIG;  // 2176
+constexpr int D_PROJ1 = 4 * D_VIS;     // 8704
+constexpr int D_LLM = 896, I_LLM = 4864, QKV_LLM = 1152, HQ = 14, HKV = 2;
+constexpr int N_AQ = 64;
+constexpr int KP = 592;  // patch vector (588) padded to a multiple of 8
+constexpr int PKV = 1792;
+constexpr float LLM_EPS = 1e-6f, VIT_EPS = 1e-6f, HEAD_EPS = 1e-5f, ROPE_THETA = 1e6f;
+
+struct Master {
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  size_t n = 0;
+};
+
+struct VitBlock {
+  float *ln1w, *ln1b, *bqkv, *bproj, *ls1, *ln2w, *ln2b, *bfc1, *bfc2, *ls2;
+  bf16 *wqkv, *wproj, *wfc1, *wfc2;
+};
+struct Tower {
+  int D, F, heads, hd, tokens, prefix, depth;
+  bf16* wpatch;
+  float* bpatch;
+  bf16* pos;
+  bf16* prefix_rows;
+  std::vector<VitBlock> blocks;
+};
+struct LlmLayer {
+  float *ln1, *bqkv, *ln2;
+  bf16 *wqkv, *wo, *wgu, *wdown;
+};
+struct HeadBlock {
+  bf16 *wqkv_self, *wkv_cond, *wkv_vis, *wo, *wffn;
+  float *bqkv_self, *bkv_cond, *bkv_vis, *bo, *ffn_lnw, *ffn_lnb, *bffn;
+  float gate;
+};
+
+__global__ void cvt_to_f32_kernel(const void* src, int dtype, float* dst, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (dtype == VLA_BF16) dst[i] = __bfloat162float(static_cast<const bf16*>(src)[i]);
+  else if (dtype == VLA_F16) dst[i] = __half2float(static_cast<const __half*>(src)[i]);
+  else dst[i] = static_cast<const float*>(src)[i];
+}
+
+// dst[(r / group) * stride + offset + r % group, c] = bf16(src[r, c])
+__global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int cols, bf16* __restrict__ dst,
+                                 int dst_ld, int group, int stride, int offset) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * cols) return;
+  const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+  const int dr = (r / group) * stride + offset + r % group;
+  dst[static_cast<size_t>(dr) * dst_ld + c] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace
+
+struct vla_engine {
+  vla_cfg cfg;
+  std::string err;
+  bool finalized = false;
+  std::unordered_map<std::string, Master> masters;
+  std::vector<void*> allocs;
+
+  // derived
+  int NP = 0, T = 0, A = 0, P = 0;
+  Tower dino, sig;
+  bf16 *pj_w1, *pj_w2, *pj_w3;
+  float *pj_b1, *pj_b2, *pj_b3;
+  bf16 *embed, *aq_table;
+  std::vector<LlmLayer> llm;
+  float* llm_norm;
+  float *rope_cos = nullptr, *rope_sin = nullptr;
+  // head
+  std::vector<HeadBlock> head;
+  bf16 *x0, *wkv_p_all, *head_fc2_w, *pp_w1, *pp_w2;
+  float *bkv_p_all, *head_ln2w, *head_ln2b, *head_fc2_b, *pp_b1, *pp_b2;
+  float *prope_cos = nullptr, *prope_sin = nullptr;
+  float *st_hi = nullptr, *st_lo = nullptr;
+  uint8_t* st_mask = nullptr;
+  bool stats_set = false;
+
+  // workspace
+  int maxB = 0, maxL = 0, maxS = 0;
+  bf16 *w_col, *w_x, *w_xn, *w_qkv, *w_attn, *w_h, *w_patches, *w_ph1, *w_ph2;
+  std::vector<bf16*> hid;  // 25 LLM states
+  bf16 *l_tmp, *l_xn, *l_qkv, *l_attn, *l_act;
+  bf16 *h_p1, *h_p, *h_pkv, *h_kva, *h_kvt, *h_qkv, *h_ao, *h_y, *h_yn;
+  std::vector<bf16*> head_x;  // 25 policy states
+  int* err_flag = nullptr;
+  // pinned/dev staging for vla_predict_host
+  void *pin_pix = nullptr, *pin_ids = nullptr, *pin_aq = nullptr, *pin_prop = nullptr, *pin_out = nullptr,
+       *pin_ha = nullptr;
+  void *dev_pix = nullptr, *dev_ids = nullptr, *dev_aq = nullptr, *dev_prop = nullptr, *dev_out = nullptr,
+       *dev_ha = nullptr;
+
+  // last call
+  int lastB = 0, lastL = 0;
+  long long last_launches = 0;
+
+  int fail(int code, const std::string& m) {
+    err = m;
+    return code;
+  }
+  template <class Tp>
+  Tp* dalloc(size_t count) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(Tp);
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      throw std::runtime_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+    }
+    allocs.push_back(p);
+    return static_cast<Tp*>(p);
+  }
+  const Master& need(const std::string& name, size_t numel) {
+    auto it = masters.find(name);
+    if (it == masters.end()) throw std::runtime_error("missing tensor: " + name);
+    if (it->second.n != numel)
+      throw std::runtime_error("tensor " + name + " has " + std::to_string(it->second.n) + " elements, expected " +
+                               std::to_string(numel));
+    return it->second;
+  }
+  float* f32(const std::string& name, size_t numel) { return need(name, numel).d; }
+  // pack one [rows, cols] fp32 master into dst (bf16) at a row mapping
+  void pack_into(bf16* dst, int dst_ld, const std::string& name, int rows, int cols, int group, int stride,
+                 int offset) {
+    const Master& m = need(name, static_cast<size_t>(rows) * cols);
+    const size_t n = static_cast<size_t>(rows) * cols;
+    pack_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(m.d, rows, cols, dst, dst_ld, group, stride,
+                                                                    offset);
+  }
+  bf16* pack(const std::string& name, int rows, int cols, int dst_ld = 0) {
+    if (!dst_ld) dst_ld = cols;
+    bf16* dst = dalloc<bf16>(static_cast<size_t>(rows) * dst_ld);
+    if (dst_ld != cols) cudaMemset(dst, 0, static_cast<size_t>(rows) * dst_ld * sizeof(bf16));
+    pack_into(dst, dst_ld, name, rows, cols, rows, 0, 0);
+    return dst;
+  }
+  // concatenates [name_i (rows_i x cols)] along rows
+  bf16* pack_cat(const std::vector<std::pair<std::string, int>>& parts, int cols) {
+    int total = 0;
+    for (auto& p : parts) total += p.second;
+    bf16* dst = dalloc<bf16>(static_cast<size_t>(total) * cols);
+    int off = 0;
+    for (auto& p : parts) {
+      pack_into(dst, cols, p.first, p.second, cols, p.second, 0, off);
+      off += p.second;
+    }
+    return dst;
+  }
+  float* cat_f32(const std::vector<std::pair<std::string, int>>& parts) {
+    int total = 0;
+    for (auto& p : parts) total += p.second;
+    float* dst = dalloc<float>(total);
+    int off = 0;
+    for (auto& p : parts) {
+      cudaMemcpy(dst + off, need(p.first, p.second).d, sizeof(float) * p.second, cudaMemcpyDeviceToDevice);
+      off += p.second;
+    }
+    return dst;
+  }
+};
+
+namespace {
+
+bool ignored_name(const std::string& n) {
+  static const char* pats[] = {"lm_head.", "film_gen.", "attn_pool.", "featurizer.norm.", "inv_freq",
+                               "noisy_action", "rope."};
+  for (const char* p : pats)
+    if (n.find(p) != std::string::npos) return true;
+  return false;
+}
+
+void build_tower(vla_engine* e, Tower& t, const std::string& pfx, bool is_dino, int depth) {
+  t.D = is_dino ? D_DINO : D_SIG;
+  t.F = is_dino ? F_DINO : F_SIG;
+  t.heads = 16;
+  t.hd = t.D / 16;
+  t.tokens = is_dino ? TOK_DINO : TOK_SIG;
+  t.prefix = is_dino ? PRE_DINO : 0;
+  t.depth = depth;
+  const int D = t.D, F = t.F;
+  t.wpatch = e->pack(pfx + "patch_embed.proj.weight", D, 588, KP);
+  t.bpatch = e->f32(pfx + "patch_embed.proj.bias", D);
+  t.pos = e->pack(pfx + "pos_embed", 256, D);
+  t.prefix_rows = nullptr;
+  if (is_dino) t.prefix_rows = e->pack_cat({{pfx + "cls_token", 1}, {pfx + "reg_token", 4}}, D);
+  // Only blocks 0 .. depth-2 contribute to the output (modeling_prismatic.py:141-142).
+  for (int i = 0; i <= depth - 2; ++i) {
+    const std::string b = pfx + "blocks." + std::to_string(i) + ".";
+    VitBlock k;
+    k.ln1w = e->f32(b + "norm1.weight", D);
+    k.ln1b = e->f32(b + "norm1.bias", D);
+    k.wqkv = e->pack(b + "attn.qkv.weight", 3 * D, D);
+    k.bqkv = e->f32(b + "attn.qkv.bias", 3 * D);
+    k.wproj = e->pack(b + "attn.proj.weight", D, D);
+    k.bproj = e->f32(b + "attn.proj.bias", D);
+    k.ls1 = is_dino ? e->f32(b + "ls1.scale_factor", D) : nullptr;
+    k.ln2w = e->f32(b + "norm2.weight", D);
+    k.ln2b = e->f32(b + "norm2.bias", D);
+    k.wfc1 = e->pack(b + "mlp.fc1.weight", F, D);
+    k.bfc1 = e->f32(b + "mlp.fc1.bias", F);
+    k.wfc2 = e->pack(b + "mlp.fc2.weight", D, F);
+    k.bfc2 = e->f32(b + "mlp.fc2.bias", D);
+    k.ls2 = is_dino ? e->f32(b + "ls2.scale_factor", D) : nullptr;
+    t.blocks.push_back(k);
+  }
+}
+
+#define CK(call)                                   \
+  do {                                             \
+    const char* _err = nullptr;                    \
+    int _rc = (call);                              \
+    if (_rc) return e->fail(_rc, _err ? _err : "kernel launch failed"); \
+  } while (0)
+
+int run_tower(vla_engine* e, const Tower& t, const bf16* pix, int B, int tower_idx, cudaStream_t s) {
+  const int n = e->cfg.n_images, slabs = B * n, D = t.D, F = t.F;
+  const int M = slabs * t.tokens;
+  bf16* x = e->w_x;
+  CK(vla::im2col_launch(pix, B, n, tower_idx, e->w_col, s, &_err));
+  if (t.prefix) CK(vla::prefix_tokens_launch(x, slabs, static_cast<long long>(t.tokens) * D, D, t.prefix_rows, t.prefix, s, &_err));
+  {
+    // patch embed (+bias +pos_embed) written behind the prefix rows of every image slab
+    vla::GemmArgs g;
+    g.A = e->w_col; g.a_batch_stride = 256LL * KP; g.lda = KP; g.rows = 256; g.batches = slabs;
+    g.W = t.wpatch; g.ldw = KP; g.N = D; g.K = KP;
+    g.C = x + static_cast<long long>(t.prefix) * D; g.c_batch_stride = static_cast<long long>(t.tokens) * D; g.ldc = D;
+    g.bias = t.bpatch; g.resid = t.pos; g.r_batch_stride = 0; g.ldr = D;
+    CK(vla::gemm_launch(g, s, &_err));
+  }
+  const int nblk = static_cast<int>(t.blocks.size());
+  for (int i = 0; i < nblk; ++i) {
+    const VitBlock& k = t.blocks[i];
+    const bool last = (i == nblk - 1);
+    CK(vla::layernorm_launch(x, M, D, D, k.ln1w, k.ln1b, VIT_EPS, e->w_xn, D, s, &_err));
+    vla::GemmArgs g;
+    g.A = e->w_xn; g.lda = D; g.rows = M; g.W = k.wqkv; g.ldw = D; g.N = 3 * D; g.K = D;
+    g.C = e->w_qkv; g.ldc = 3 * D; g.bias = k.bqkv;
+    CK(vla::gemm_launch(g, s, &_err));
+    CK(vla::attention_launch(e->w_qkv, 3 * D, 0, D, 2 * D, slabs, t.tokens, t.heads, 1, t.hd, 0, e->w_attn, D, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->w_attn; g.lda = D; g.rows = M; g.W = k.wproj; g.ldw = D; g.N = D; g.K = D;
+    g.C = x; g.ldc = D; g.bias = k.bproj; g.colscale = k.ls1; g.resid = x; g.ldr = D;
+    CK(vla::gemm_launch(g, s, &_err));
+    CK(vla::layernorm_launch(x, M, D, D, k.ln2w, k.ln2b, VIT_EPS, e->w_xn, D, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->w_xn; g.lda = D; g.rows = M; g.W = k.wfc1; g.ldw = D; g.N = F; g.K = D;
+    g.C = e->w_h; g.ldc = F; g.bias = k.bfc1; g.act = vla::ACT_GELU;
+    CK(vla::gemm_launch(g, s, &_err));
+    g = vla::GemmArgs();
+    g.W = k.wfc2; g.ldw = F; g.N = D; g.K = F; g.bias = k.bfc2; g.colscale = k.ls2;
+    if (!last) {
+      g.A = e->w_h; g.lda = F; g.rows = M;
+      g.C = x; g.ldc = D; g.resid = x; g.ldr = D;
+    } else {
+      // Output block: only the patch rows (prefix stripped, film_vit_wrapper.py:162) go to the
+      // feature-concatenated buffer (modeling_prismatic.py:233, 237).
+      g.A = e->w_h + static_cast<long long>(t.prefix) * F; g.a_batch_stride = static_cast<long long>(t.tokens) * F;
+      g.lda = F; g.rows = 256; g.batches = slabs;
+      g.resid = x + static_cast<long long>(t.prefix) * D; g.r_batch_stride = static_cast<long long>(t.tokens) * D; g.ldr = D;
+      g.C = e->w_patches + (tower_idx == 0 ? 0 : D_DINO); g.c_batch_stride = 256LL * D_VIS; g.ldc = D_VIS;
+    }
+    CK(vla::gemm_launch(g, s, &_err));
+  }
+  return 0;
+}
+
+int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_t* aq_index, const float* proprio,
+            int B, int L, float* out_norm, float* out_unnorm, bf16* out_last_ha, cudaStream_t s) {
+  const int NP = e->NP, T = e->T, A = e->A, P = e->P;
+  const int Lext = L + N_AQ + 1;
+  const int S = NP + Lext;
+  const int M = B * S;
+  const int NL = e->cfg.llm_layers;
+
+  // ---------------- vision towers + projector (MP:196-237, 261-273)
+  int rc = run_tower(e, e->dino, pix, B, 0, s);
+  if (rc) return rc;
+  rc = run_tower(e, e->sig, pix, B, 1, s);
+  if (rc) return rc;
+  {
+    vla::GemmArgs g;
+    g.A = e->w_patches; g.lda = D_VIS; g.rows = B * NP; g.W = e->pj_w1; g.ldw = D_VIS; g.N = D_PROJ1; g.K = D_VIS;
+    g.C = e->w_ph1; g.ldc = D_PROJ1; g.bias = e->pj_b1; g.act = vla::ACT_GELU;
+    CK(vla::gemm_launch(g, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->w_ph1; g.lda = D_PROJ1; g.rows = B * NP; g.W = e->pj_w2; g.ldw = D_PROJ1; g.N = D_LLM; g.K = D_PROJ1;
+    g.C = e->w_ph2; g.ldc = D_LLM; g.bias = e->pj_b2; g.act = vla::ACT_GELU;
+    CK(vla::gemm_launch(g, s, &_err));
+    // fc3 writes straight into rows 1..NP of every sample's LLM input (MP:500-502)
+    g = vla::GemmArgs();
+    g.A = e->w_ph2; g.a_batch_stride = static_cast<long long>(NP) * D_LLM; g.lda = D_LLM; g.rows = NP; g.batches = B;
+    g.W = e->pj_w3; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
+    g.C = e->hid[0] + D_LLM; g.c_batch_stride = static_cast<long long>(S) * D_LLM; g.ldc = D_LLM; g.bias = e->pj_b3;
+    CK(vla::gemm_launch(g, s, &_err));
+  }
+
+  // ---------------- LLM input assembly + prefill (MP:418-454, 500-502, 834-845)
+  CK(vla::assemble_launch(e->hid[0], B, S, NP, Lext, D_LLM, ext_ids, aq_index, e->embed, e->cfg.vocab_size,
+                          e->aq_table, N_AQ, e->err_flag, s, &_err));
+  for (int l = 0; l < NL; ++l) {
+    const LlmLayer& w = e->llm[l];
+    const bf16* xin = e->hid[l];
+    bf16* xout = (l == NL - 1) ? e->l_tmp : e->hid[l + 1];
+    CK(vla::rmsnorm_launch(xin, M, D_LLM, D_LLM, w.ln1, LLM_EPS, e->l_xn, D_LLM, s, &_err));
+    vla::GemmArgs g;
+    g.A = e->l_xn; g.lda = D_LLM; g.rows = M; g.W = w.wqkv; g.ldw = D_LLM; g.N = QKV_LLM; g.K = D_LLM;
+    g.C = e->l_qkv; g.ldc = QKV_LLM; g.bias = w.bqkv;
+    CK(vla::gemm_launch(g, s, &_err));
+    CK(vla::rope_apply_launch(e->l_qkv, QKV_LLM, 0, HQ + HKV, B, S, e->rope_cos, e->rope_sin, s, &_err));
+    CK(vla::attention_launch(e->l_qkv, QKV_LLM, 0, HQ * 64, (HQ + HKV) * 64, B, S, HQ, HQ / HKV, 64, e->cfg.causal,
+                             e->l_attn, D_LLM, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->l_attn; g.lda = D_LLM; g.rows = M; g.W = w.wo; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
+    g.C = xout; g.ldc = D_LLM; g.resid = xin; g.ldr = D_LLM;
+    CK(vla::gemm_launch(g, s, &_err));
+    CK(vla::rmsnorm_launch(xout, M, D_LLM, D_LLM, w.ln2, LLM_EPS, e->l_xn, D_LLM, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->l_xn; g.lda = D_LLM; g.rows = M; g.W = w.wgu; g.ldw = D_LLM; g.N = 2 * I_LLM; g.K = D_LLM;
+    g.C = e->l_act; g.ldc = I_LLM; g.act = vla::ACT_SWIGLU;
+    CK(vla::gemm_launch(g, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->l_act; g.lda = I_LLM; g.rows = M; g.W = w.wdown; g.ldw = I_LLM; g.N = D_LLM; g.K = I_LLM;
+    g.C = xout; g.ldc = D_LLM; g.resid = xout; g.ldr = D_LLM;
+    CK(vla::gemm_launch(g, s, &_err));
+  }
+  // hidden_states[-1] is the post-final-norm state (HF output_hidden_states semantics)
+  CK(vla::rmsnorm_launch(e->l_tmp, M, D_LLM, D_LLM, e->llm_norm, LLM_EPS, e->hid[NL], D_LLM, s, &_err));
+
+  // ---------------- Bridge-Attention policy (AH:43-81, 111-121, 218-283 / 337-410)
+  CK(vla::skinny_linear_launch(proprio, 1, P, B, P, e->pp_w1, P, D_LLM, e->pp_b1, 1, e->h_p1, D_LLM, nullptr, s, &_err));
+  CK(vla::skinny_linear_launch(e->h_p1, 0, D_LLM, B, D_LLM, e->pp_w2, D_LLM, D_LLM, e->pp_b2, 0, e->h_p, D_LLM, nullptr, s, &_err));
+  const int NB = static_cast<int>(e->head.size());
+  {
+    vla::GemmArgs g;
+    g.A = e->h_p; g.lda = D_LLM; g.rows = B; g.W = e->wkv_p_all; g.ldw = D_LLM; g.N = NB * PKV; g.K = D_LLM;
+    g.C = e->h_pkv; g.ldc = NB * PKV; g.bias = e->bkv_p_all;
+    CK(vla::gemm_launch(g, s, &_err));
+  }
+  CK(vla::broadcast_row_launch(e->x0, D_LLM, B * T, e->head_x[0], s, &_err));
+  const int ha_row0 = NP + L - 1;  // MP:855 with NUM_PROMPT_TOKENS = L-1 (MP:927)
+  for (int i = 0; i < NB; ++i) {
+    const HeadBlock& w = e->head[i];
+    const bf16* hs = e->hid[i + 1];  // AH:118: block i reads hidden state i+1
+    vla::GemmArgs g;
+    g.A = hs + static_cast<long long>(ha_row0) * D_LLM; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM;
+    g.rows = N_AQ; g.batches = B; g.W = w.wkv_cond; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
+    g.C = e->h_kva; g.c_batch_stride = static_cast<long long>(N_AQ) * PKV; g.ldc = PKV; g.bias = w.bkv_cond;
+    CK(vla::gemm_launch(g, s, &_err));
+    g = vla::GemmArgs();
+    g.A = hs; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM; g.rows = NP; g.batches = B;
+    g.W = w.wkv_vis; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
+    g.C = e->h_kvt; g.c_batch_stride = static_cast<long long>(NP) * PKV; g.ldc = PKV; g.bias = w.bkv_vis;
+    CK(vla::gemm_launch(g, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->head_x[i]; g.lda = D_LLM; g.rows = B * T; g.W = w.wqkv_self; g.ldw = D_LLM; g.N = 3 * D_LLM; g.K = D_LLM;
+    g.C = e->h_qkv; g.ldc = 3 * D_LLM; g.bias = w.bqkv_self;
+    CK(vla::gemm_launch(g, s, &_err));
+    vla::PolicyAttnArgs pa;
+    pa.qkv_self = e->h_qkv; pa.kv_a = e->h_kva; pa.kv_p = e->h_pkv + static_cast<long long>(i) * PKV; pa.ld_p = NB * PKV;
+    pa.kv_t = e->h_kvt; pa.B = B; pa.T = T; pa.NP = NP; pa.gate = w.gate; pa.pro = e->cfg.variant == VLA_HEAD_PRO;
+    pa.rope_cos = e->prope_cos; pa.rope_sin = e->prope_sin; pa.out = e->h_ao;
+    CK(vla::policy_attention_launch(pa, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->h_ao; g.lda = D_LLM; g.rows = B * T; g.W = w.wo; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
+    g.C = e->h_y; g.ldc = D_LLM; g.bias = w.bo; g.resid = e->head_x[i]; g.ldr = D_LLM;
+    CK(vla::gemm_launch(g, s, &_err));
+    CK(vla::layernorm_launch(e->h_y, B * T, D_LLM, D_LLM, w.ffn_lnw, w.ffn_lnb, HEAD_EPS, e->h_yn, D_LLM, s, &_err));
+    g = vla::GemmArgs();
+    g.A = e->h_yn; g.lda = D_LLM; g.rows = B * T; g.W = w.wffn; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
+    g.C = e->head_x[i + 1]; g.ldc = D_LLM; g.bias = w.bffn; g.act = vla::ACT_RELU;
+    CK(vla::gemm_launch(g, s, &_err));
+  }
+  CK(vla::head_out_launch(e->head_x[NB], B * T, e->head_ln2w, e->head_ln2b, e->head_fc2_w, e->head_fc2_b, A,
+                          e->st_hi, e->st_lo, e->st_mask, out_norm, out_unnorm, s, &_err));
+  if (out_last_ha)
+    CK(vla::gather_rows_launch(e->hid[NL], static_cast<long long>(S) * D_LLM, D_LLM, ha_row0, N_AQ, B, D_LLM,
+                               out_last_ha, s, &_err));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vla_create(const vla_cfg* cfg, vla_engine** out) {
+  if (!cfg || !out) return VLA_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return VLA_ERR_CUDA;  // no CPU fallback
+  }
+  vla_engine* e = new vla_engine();
+  e->cfg = *cfg;
+  *out = e;
+  const vla_cfg& c = e->cfg;
+  if (c.n_images < 1 || c.n_images > 3) return e->fail(VLA_ERR_INVALID, "n_images must be 1..3");
+  if (c.chunk_len < 1 || c.chunk_len > 32) return e->fail(VLA_ERR_INVALID, "chunk_len must be 1..32");
+  if (c.action_dim < 1 || c.action_dim > 64) return e->fail(VLA_ERR_INVALID, "action_dim must be 1..64");
+  if (c.proprio_dim < 1 || c.proprio_dim > 1024) return e->fail(VLA_ERR_INVALID, "proprio_dim must be 1..1024");
+  if (c.variant != VLA_HEAD_BASE && c.variant != VLA_HEAD_PRO) return e->fail(VLA_ERR_INVALID, "unknown head variant");
+  if (c.dino_depth < 2 || c.siglip_depth < 2) return e->fail(VLA_ERR_INVALID, "ViT depth must be >= 2");
+  if (c.llm_layers != 24)
+    return e->fail(VLA_ERR_INVALID, "llm_layers must be 24: MLPResNet has 24 blocks, block i reads state i+1 (AH:36,118)");
+  if (c.vocab_size < 3) return e->fail(VLA_ERR_INVALID, "vocab_size must cover the placeholder/stop ids");
+  if (c.max_batch < 1 || c.max_prompt_len < 1) return e->fail(VLA_ERR_INVALID, "max_batch/max_prompt_len must be >= 1");
+  e->NP = 256 * c.n_images;
+  e->T = c.chunk_len;
+  e->A = c.action_dim;
+  e->P = c.proprio_dim;
+  return VLA_OK;
+}
+
+int vla_load_tensor(vla_engine* e, const char* name, const void* ptr, int dtype, int ndim, const int64_t* shape) {
+  if (!e) return VLA_ERR_INVALID;
+  if (!name || !ptr || ndim < 0 || ndim > 8 || (ndim && !shape)) return e->fail(VLA_ERR_INVALID, "load_tensor: bad argument");
+  if (e->finalized) return e->fail(VLA_ERR_INVALID, "load_tensor after finalize");
+  std::string n(name);
+  if (n.rfind("vla.", 0) != 0 && n.rfind("head.", 0) != 0 && n.rfind("proprio.", 0) != 0)
+    return e->fail(VLA_ERR_INVALID, "unknown tensor name (expected vla./head./proprio. prefix): " + n);
+  if (dtype != VLA_BF16 && dtype != VLA_F32 && dtype != VLA_F16) return e->fail(VLA_ERR_DTYPE, "unsupported dtype for " + n);
+  if (ignored_name(n)) return VLA_OK;
+  size_t numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 0) return e->fail(VLA_ERR_INVALID, "negative dimension in " + n);
+    numel *= static_cast<size_t>(shape[i]);
+  }
+  if (numel == 0) return e->fail(VLA_ERR_INVALID, "empty tensor " + n);
+  const size_t esz = dtype == VLA_F32 ? 4 : 2;
+  cudaPointerAttributes attr;
+  bool on_device = false;
+  if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess) on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+  cudaGetLastError();
+  const void* src = ptr;
+  void* staging = nullptr;
+  if (!on_device) {
+    if (cudaMalloc(&staging, numel * esz) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "cudaMalloc failed for staging " + n);
+    if (cudaMemcpy(staging, ptr, numel * esz, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(staging);
+      return e->fail(VLA_ERR_CUDA, "H2D copy failed for " + n);
+    }
+    src = staging;
+  }
+  Master m;
+  m.n = numel;
+  m.shape.assign(shape, shape + ndim);
+  auto old = e->masters.find(n);
+  if (old != e->masters.end() && old->second.n == numel) {
+    m.d = old->second.d;
+  } else {
+    if (cudaMalloc(&m.d, numel * sizeof(float)) != cudaSuccess) {
+      if (staging) cudaFree(staging);
+      return e->fail(VLA_ERR_CUDA, "cudaMalloc failed for " + n);
+    }
+    e->allocs.push_back(m.d);
+  }
+  cvt_to_f32_kernel<<<static_cast<unsigned>((numel + 255) / 256), 256>>>(src, dtype, m.d, numel);
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (staging) cudaFree(staging);
+  if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("convert failed: ") + cudaGetErrorString(ce));
+  e->masters[n] = m;
+  return VLA_OK;
+}
+
+int vla_set_action_stats(vla_engine* e, const double* hi, const double* lo, const uint8_t* mask) {
+  if (!e) return VLA_ERR_INVALID;
+  if (!hi || !lo) return e->fail(VLA_ERR_INVALID, "set_action_stats: null statistics");
+  const int A = e->A;
+  std::vector<float> fh(A), fl(A);
+  std::vector<uint8_t> fm(A, 1);
+  for (int i = 0; i < A; ++i) {
+    fh[i] = static_cast<float>(hi[i]);
+    fl[i] = static_cast<float>(lo[i]);
+    if (mask) fm[i] = mask[i] ? 1 : 0;
+  }
+  try {
+    if (!e->st_hi) {
+      e->st_hi = e->dalloc<float>(A);
+      e->st_lo = e->dalloc<float>(A);
+      e->st_mask = e->dalloc<uint8_t>(A);
+    }
+  } catch (const std::exception& ex) {
+    return e->fail(VLA_ERR_CUDA, ex.what());
+  }
+  cudaMemcpy(e->st_hi, fh.data(), A * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(e->st_lo, fl.data(), A * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(e->st_mask, fm.data(), A, cudaMemcpyHostToDevice);
+  e->stats_set = true;
+  return VLA_OK;
+}
+
+int vla_finalize(vla_engine* e) {
+  if (!e) return VLA_ERR_INVALID;
+  if (e->finalized) return VLA_OK;
+  const vla_cfg& c = e->cfg;
+  try {
+    if (!e->stats_set) {
+      std::vector<double> hi(e->A, 1.0), lo(e->A, -1.0);
+      int rc = vla_set_action_stats(e, hi.data(), lo.data(), nullptr);
+      if (rc) return rc;
+    }
+    build_tower(e, e->dino, "vla.vision_backbone.featurizer.", true, c.dino_depth);
+    build_tower(e, e->sig, "vla.vision_backbone.fused_featurizer.", false, c.siglip_depth);
+    e->pj_w1 = e->pack("vla.projector.fc1.weight", D_PROJ1, D_VIS);
+    e->pj_b1 = e->f32("vla.projector.fc1.bias", D_PROJ1);
+    e->pj_w2 = e->pack("vla.projector.fc2.weight", D_LLM, D_PROJ1);
+    e->pj_b2 = e->f32("vla.projector.fc2.bias", D_LLM);
+    e->pj_w3 = e->pack("vla.projector.fc3.weight", D_LLM, D_LLM);
+    e->pj_b3 = e->f32("vla.projector.fc3.bias", D_LLM);
+
+    const std::string lm = "vla.language_model.model.";
+    e->embed = e->pack(lm + "embed_tokens.weight", c.vocab_size, D_LLM);
+    e->aq_table = e->pack("vla.action_queries.weight", N_AQ, D_LLM);
+    for (int l = 0; l < c.llm_layers; ++l) {
+      const std::string b = lm + "layers." + std::to_string(l) + ".";
+      LlmLayer w;
+      w.ln1 = e->f32(b + "input_layernorm.weight", D_LLM);
+      w.wqkv = e->pack_cat({{b + "self_attn.q_proj.weight", HQ * 64}, {b + "self_attn.k_proj.weight", HKV * 64}, {b + "self_attn.v_proj.weight", HKV * 64}}, D_LLM);
+      w.bqkv = e->cat_f32({{b + "self_attn.q_proj.bias", HQ * 64}, {b + "self_attn.k_proj.bias", HKV * 64}, {b + "self_attn.v_proj.bias", HKV * 64}});
+      w.wo = e->pack(b + "self_attn.o_proj.weight", D_LLM, D_LLM);
+      w.ln2 = e->f32(b + "post_attention_layernorm.weight", D_LLM);
+      // gate/up rows interleaved in groups of 16 for the SwiGLU epilogue
+      w.wgu = e->dalloc<bf16>(static_cast<size_t>(2 * I_LLM) * D_LLM);
+      e->pack_into(w.wgu, D_LLM, b + "mlp.gate_proj.weight", I_LLM, D_LLM, 16, 32, 0);
+      e->pack_into(w.wgu, D_LLM, b + "mlp.up_proj.weight", I_LLM, D_LLM, 16, 32, 16);
+      w.wdown = e->pack(b + "mlp.down_proj.weight", D_LLM, I_LLM);
+      e->llm.push_back(w);
+    }
+    e->llm_norm = e->f32(lm + "norm.weight", D_LLM);
+
+    // ---- policy head
+    const bool pro = c.variant == VLA_HEAD_PRO;
+    const std::string hm = "head.model.";
+    const int in_dim = e->A * D_LLM;  // MLPResNet input_dim = input_dim * ACTION_DIM (AH:37)
+    std::vector<std::pair<std::string, int>> pw, pb;
+    std::vector<float> gates(24, 0.f);
+    for (int i = 0; i < 24; ++i) {
+      const std::string b = hm + "mlp_resnet_blocks." + std::to_string(i) + ".";
+      HeadBlock w;
+      const std::string ks = pro ? "k_self" : "k_proj", vs = pro ? "v_self" : "v_proj";
+      const std::string kc = pro ? "k_adapter" : "k_proj", vc = pro ? "v_adapter" : "v_proj";
+      const std::string kv = pro ? "k_task" : "k_proj", vv = pro ? "v_task" : "v_proj";
+      w.wqkv_self = e->pack_cat({{b + "q_proj.weight", D_LLM}, {b + ks + ".weight", D_LLM}, {b + vs + ".weight", D_LLM}}, D_LLM);
+      w.bqkv_self = e->cat_f32({{b + "q_proj.bias", D_LLM}, {b + ks + ".bias", D_LLM}, {b + vs + ".bias", D_LLM}});
+      w.wkv_cond = e->pack_cat({{b + kc + ".weight", D_LLM}, {b + vc + ".weight", D_LLM}}, D_LLM);
+      w.bkv_cond = e->cat_f32({{b + kc + ".bias", D_LLM}, {b + vc + ".bias", D_LLM}});
+      if (pro) {
+        w.wkv_vis = e->pack_cat({{b + kv + ".weight", D_LLM}, {b + vv + ".weight", D_LLM}}, D_LLM);
+        w.bkv_vis = e->cat_f32({{b + kv + ".bias", D_LLM}, {b + vv + ".bias", D_LLM}});
+      } else {
+        w.wkv_vis = w.wkv_cond;
+        w.bkv_vis = w.bkv_cond;
+      }
+      w.wo = e->pack(b + "o_proj.weight", D_LLM, D_LLM);
+      w.bo = e->f32(b + "o_proj.bias", D_LLM);
+      w.ffn_lnw = e->f32(b + "ffn.0.weight", D_LLM);
+      w.ffn_lnb = e->f32(b + "ffn.0.bias", D_LLM);
+      w.wffn = e->pack(b + "ffn.1.weight", D_LLM, D_LLM);
+      w.bffn = e->f32(b + "ffn.1.bias", D_LLM);
+      float g = 0.f;
+      cudaMemcpy(&g, e->f32(b + "gating_factor", 1), sizeof(float), cudaMemcpyDeviceToHost);
+      // ratio_g = tanh(g) evaluated in the parameter dtype (bf16), AH:225 / AH:344
+      const float gb = __bfloat162float(__float2bfloat16_rn(g));
+      w.gate = __bfloat162float(__float2bfloat16_rn(std::tanh(gb)));
+      pw.push_back({b + kc + ".weight", D_LLM});
+      pw.push_back({b + vc + ".weight", D_LLM});
+      pb.push_back({b + kc + ".bias", D_LLM});
+      pb.push_back({b + vc + ".bias", D_LLM});
+      e->head.push_back(w);
+    }
+    e->wkv_p_all = e->pack_cat(pw, D_LLM);
+    e->bkv_p_all = e->cat_f32(pb);
+    e->head_ln2w = e->f32(hm + "layer_norm2.weight", D_LLM);
+    e->head_ln2b = e->f32(hm + "layer_norm2.bias", D_LLM);
+    e->head_fc2_w = e->pack(hm + "fc2.weight", e->A, D_LLM);
+    e->head_fc2_b = e->f32(hm + "fc2.bias", e->A);
+    e->pp_w1 = e->pack("proprio.fc1.weight", D_LLM, e->P);
+    e->pp_b1 = e->f32("proprio.fc1.bias", D_LLM);
+    e->pp_w2 = e->pack("proprio.fc2.weight", D_LLM, D_LLM);
+    e->pp_b2 = e->f32("proprio.fc2.bias", D_LLM);
+    // x0 = ReLU(fc1(LayerNorm(0))) = ReLU(fc1.W @ bf16(ln1.bias) + fc1.b): input independent (AH:60-67, 114-116)
+    {
+      bf16* wfc1 = e->pack(hm + "fc1.weight", D_LLM, in_dim);
+      e->x0 = e->dalloc<bf16>(D_LLM);
+      const char* err = nullptr;
+      e->need(hm + "layer_norm1.weight", in_dim);
+      int rc = vla::skinny_linear_launch(e->f32(hm + "layer_norm1.bias", in_dim), 1, in_dim, 1, in_dim, wfc1, in_dim,
+                                         D_LLM, e->f32(hm + "fc1.bias", D_LLM), 2, e->x0, D_LLM, nullptr, 0, &err);
+      if (rc) return e->fail(rc, err ? err : "x0 precompute failed");
+    }
+
+    // ---- workspace
+    const int B = c.max_batch, L = c.max_prompt_len, n = c.n_images;
+    const int S = e->NP + L + N_AQ + 1;
+    e->maxB = B; e->maxL = L; e->maxS = S;
+    const size_t slabs = static_cast<size_t>(B) * n;
+    const size_t Mv = slabs * TOK_DINO;
+    e->w_col = e->dalloc<bf16>(slabs * 256 * KP);
+    e->w_x = e->dalloc<bf16>(Mv * D_SIG);
+    e->w_xn = e->dalloc<bf16>(Mv * D_SIG);
+    e->w_qkv = e->dalloc<bf16>(Mv * 3 * D_SIG);
+    e->w_attn = e->dalloc<bf16>(Mv * D_SIG);
+    e->w_h = e->dalloc<bf16>(Mv * F_SIG);
+    e->w_patches = e->dalloc<bf16>(slabs * 256 * D_VIS);
+    e->w_ph1 = e->dalloc<bf16>(slabs * 256 * D_PROJ1);
+    e->w_ph2 = e->dalloc<bf16>(slabs * 256 * D_LLM);
+    const size_t Ml = static_cast<size_t>(B) * S;
+    for (int i = 0; i <= c.llm_layers; ++i) e->hid.push_back(e->dalloc<bf16>(Ml * D_LLM));
+    e->l_tmp = e->dalloc<bf16>(Ml * D_LLM);
+    e->l_xn = e->dalloc<bf16>(Ml * D_LLM);
+    e->l_qkv = e->dalloc<bf16>(Ml * QKV_LLM);
+    e->l_attn = e->dalloc<bf16>(Ml * D_LLM);
+    e->l_act = e->dalloc<bf16>(Ml * I_LLM);
+    const size_t BT = static_cast<size_t>(B) * e->T;
+    e->h_p1 = e->dalloc<bf16>(static_cast<size_t>(B) * D_LLM);
+    e->h_p = e->dalloc<bf16>(static_cast<size_t>(B) * D_LLM);
+    e->h_pkv = e->dalloc<bf16>(static_cast<size_t>(B) * 24 * PKV);
+    e->h_kva = e->dalloc<bf16>(static_cast<size_t>(B) * N_AQ * PKV);
+    e->h_kvt = e->dalloc<bf16>(static_cast<size_t>(B) * e->NP * PKV);
+    e->h_qkv = e->dalloc<bf16>(BT * 3 * D_LLM);
+    e->h_ao = e->dalloc<bf16>(BT * D_LLM);
+    e->h_y = e->dalloc<bf16>(BT * D_LLM);
+    e->h_yn = e->dalloc<bf16>(BT * D_LLM);
+    for (int i = 0; i <= 24; ++i) e->head_x.push_back(e->dalloc<bf16>(BT * D_LLM));
+    e->err_flag = e->dalloc<int>(1);
+    cudaMemset(e->err_flag, 0, sizeof(int));
+    e->rope_cos = e->dalloc<float>(static_cast<size_t>(S) * 32);
+    e->rope_sin = e->dalloc<float>(static_cast<size_t>(S) * 32);
+    const char* err = nullptr;
+    int rc = vla::rope_table_launch(e->rope_cos, e->rope_sin, S, 32, ROPE_THETA, 0, &err);
+    if (rc) return e->fail(rc, err ? err : "rope table failed");
+    const int max_pos = e->NP > 65 ? e->NP : 65;
+    e->prope_cos = e->dalloc<float>(static_cast<size_t>(max_pos) * 112);
+    e->prope_sin = e->dalloc<float>(static_cast<size_t>(max_pos) * 112);
+    rc = vla::policy_rope_table_launch(e->prope_cos, e->prope_sin, max_pos, 0, &err);
+    if (rc) return e->fail(rc, err ? err : "policy rope table failed");
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("finalize: ") + cudaGetErrorString(ce));
+  } catch (const std::exception& ex) {
+    const std::string m = ex.what();
+    return e->fail(m.rfind("missing tensor", 0) == 0 ? VLA_ERR_MISSING : (m.rfind("tensor ", 0) == 0 ? VLA_ERR_INVALID : VLA_ERR_CUDA), m);
+  }
+  e->finalized = true;
+  return VLA_OK;
+}
+
+int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids, const int32_t* aq_index,
+                const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
+                void* stream) {
+  if (!e) return VLA_ERR_INVALID;
+  if (!e->finalized) return e->fail(VLA_ERR_NOT_FINALIZED, "vla_predict before vla_finalize");
+  if (!pixel_values || !ext_ids || !aq_index || !proprio || !out_norm)
+    return e->fail(VLA_ERR_INVALID, "vla_predict: null input/output pointer");
+  if (B < 1 || B > e->maxB) return e->fail(VLA_ERR_INVALID, "vla_predict: batch outside [1, max_batch]");
+  if (L < 1 || L > e->maxL) return e->fail(VLA_ERR_INVALID, "vla_predict: prompt length outside [1, max_prompt_len]");
+  const long long before = vla::gemm_launch_count() + vla::ops_launch_count();
+  int rc = forward(e, static_cast<const bf16*>(pixel_values), ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm,
+                   static_cast<bf16*>(out_last_ha), static_cast<cudaStream_t>(stream));
+  e->last_launches = vla::gemm_launch_count() + vla::ops_launch_count() - before;
+  e->lastB = B;
+  e->lastL = L;
+  return rc;
+}
+
+int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext_ids, const int32_t* aq_index,
+                     const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
+                     void* stream) {
+  if (!e) return VLA_ERR_INVALID;
+  if (!e->finalized) return e->fail(VLA_ERR_NOT_FINALIZED, "vla_predict_host before vla_finalize");
+  if (!pixel_values || !ext_ids || !aq_index || !proprio || !out_norm)
+    return e->fail(VLA_ERR_INVALID, "vla_predict_host: null input/output pointer");
+  if (B < 1 || B > e->maxB) return e->fail(VLA_ERR_INVALID, "vla_predict_host: batch outside [1, max_batch]");
+  if (L < 1 || L > e->maxL) return e->fail(VLA_ERR_INVALID, "vla_predict_host: prompt length outside [1, max_prompt_len]");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t pix_b = static_cast<size_t>(e->maxB) * 6 * e->cfg.n_images * 224 * 224 * 2;
+  const size_t ids_b = static_cast<size_t>(e->maxB) * (e->maxL + N_AQ + 1) * 8;
+  const size_t aq_b = ids_b / 2;
+  const size_t prop_b = static_cast<size_t>(e->maxB) * e->P * 4;
+  const size_t out_b = static_cast<size_t>(e->maxB) * e->T * e->A * 4;
+  const size_t ha_b = static_cast<size_t>(e->maxB) * N_AQ * D_LLM * 2;
+  if (!e->dev_pix) {
+    try {
+      e->dev_pix = e->dalloc<uint8_t>(pix_b);
+      e->dev_ids = e->dalloc<uint8_t>(ids_b);
+      e->dev_aq = e->dalloc<uint8_t>(aq_b);
+      e->dev_prop = e->dalloc<uint8_t>(prop_b);
+      e->dev_out = e->dalloc<uint8_t>(2 * out_b);
+      e->dev_ha = e->dalloc<uint8_t>(ha_b);
+    } catch (const std::exception& ex) {
+      return e->fail(VLA_ERR_CUDA, ex.what());
+    }
+  }
+  const int Lext = L + N_AQ + 1;
+  const size_t n_out = static_cast<size_t>(B) * e->T * e->A;
+  cudaError_t ce = cudaSuccess;
+  ce = cudaMemcpyAsync(e->dev_pix, pixel_values, static_cast<size_t>(B) * 6 * e->cfg.n_images * 224 * 224 * 2, cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_ids, ext_ids, static_cast<size_t>(B) * Lext * 8, cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_aq, aq_index, static_cast<size_t>(B) * Lext * 4, cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_prop, proprio, static_cast<size_t>(B) * e->P * 4, cudaMemcpyHostToDevice, s);
+  if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(ce));
+  float* d_norm = static_cast<float*>(e->dev_out);
+  float* d_un = d_norm + static_cast<size_t>(e->maxB) * e->T * e->A;
+  int rc = vla_predict(e, e->dev_pix, static_cast<const int64_t*>(e->dev_ids), static_cast<const int32_t*>(e->dev_aq),
+                       static_cast<const float*>(e->dev_prop), B, L, d_norm, d_un, out_last_ha ? e->dev_ha : nullptr, stream);
+  if (rc) return rc;
+  ce = cudaMemcpyAsync(out_norm, d_norm, n_out * 4, cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess && out_unnorm) ce = cudaMemcpyAsync(out_unnorm, d_un, n_out * 4, cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess && out_last_ha)
+    ce = cudaMemcpyAsync(out_last_ha, e->dev_ha, static_cast<size_t>(B) * N_AQ * D_LLM * 2, cudaMemcpyDeviceToHost, s);
+  int flag = 0;
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(&flag, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("predict: ") + cudaGetErrorString(ce));
+  if (flag) {
+    cudaMemset(e->err_flag, 0, sizeof(int));
+    return e->fail(VLA_ERR_INVALID, flag == 1 ? "token id outside [0, vocab_size)" : "ActionQuery index outside [0, 64)");
+  }
+  return VLA_OK;
+}
+
+int vla_get_tap(vla_engine* e, const char* name, void* dst, size_t capacity, size_t* bytes) {
+  if (!e) return VLA_ERR_INVALID;
+  if (!name || !e->lastB) return e->fail(VLA_ERR_INVALID, "get_tap: no forward has run yet");
+  const std::string n(name);
+  const int B = e->lastB, L = e->lastL, NP = e->NP;
+  const int S = NP + L + N_AQ + 1;
+  const bf16* src = nullptr;
+  size_t count = 0;
+  bool strided_proj = false;
+  if (n == "patches") { src = e->w_patches; count = static_cast<size_t>(B) * NP * D_VIS; }
+  else if (n == "projected") { strided_proj = true; count = static_cast<size_t>(B) * NP * D_LLM; }
+  else if (n == "llm_in") { src = e->hid[0]; count = static_cast<size_t>(B) * S * D_LLM; }
+  else if (n.rfind("hidden.", 0) == 0) {
+    const int i = atoi(n.c_str() + 7);
+    if (i < 0 || i > e->cfg.llm_layers) return e->fail(VLA_ERR_INVALID, "get_tap: bad hidden index");
+    src = e->hid[i]; count = static_cast<size_t>(B) * S * D_LLM;
+  } else if (n.rfind("head_x.", 0) == 0) {
+    const int i = atoi(n.c_str() + 7);
+    if (i < 0 || i > 24) return e->fail(VLA_ERR_INVALID, "get_tap: bad head_x index");
+    src = e->head_x[i]; count = static_cast<size_t>(B) * e->T * D_LLM;
+  } else return e->fail(VLA_ERR_INVALID, "get_tap: unknown tap " + n);
+  if (bytes) *bytes = count * 2;
+  if (!dst) return VLA_OK;
+  if (capacity < count * 2) return e->fail(VLA_ERR_INVALID, "get_tap: destination too small");
+  cudaError_t ce;
+  cudaDeviceSynchronize();
+  if (strided_proj) {
+    ce = cudaMemcpy2D(dst, static_cast<size_t>(NP) * D_LLM * 2, e->hid[0] + D_LLM, static_cast<size_t>(S) * D_LLM * 2,
+                      static_cast<size_t>(NP) * D_LLM * 2, B, cudaMemcpyDefault);
+  } else {
+    ce = cudaMemcpy(dst, src, count * 2, cudaMemcpyDefault);
+  }
+  if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("get_tap: ") + cudaGetErrorString(ce));
+  return VLA_OK;
+}
+
+long long vla_last_launch_count(const vla_engine* e) { return e ? e->last_launches : 0; }
+
+const char* vla_last_error(const vla_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+void vla_destroy(vla_engine* e) {
+  if (!e) return;
+  cudaDeviceSynchronize();
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+}
+
+}  // extern "C"

@@ -283,6 +283,14 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long l
       *reinterpret_cast<const uint4*>(src + b * src_bs + static_cast<long long>(r0 + r) * ld + v * 8);
 }
 
+__global__ void broadcast_row_kernel(const __nv_bfloat16* __restrict__ src, int dim, int rows,
+                                     __nv_bfloat16* __restrict__ dst) {
+  const int nvec = dim >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * nvec) return;
+  reinterpret_cast<uint4*>(dst)[idx] = __ldg(reinterpret_cast<const uint4*>(src) + (idx % nvec));
+}
+
 }  // namespace
 
 long long ops_launch_count() { return g_ops_launches.load(); }
@@ -380,6 +388,13 @@ int skinny_linear_launch(const void* x, int x_is_f32, int ldx, int M, int K, con
   const long long warps = static_cast<long long>(M) * N;
   skinny_linear_kernel<<<static_cast<int>((warps + 7) / 8), 256, 0, s>>>(x, x_is_f32, ldx, M, K, W, ldw, N,
                                                                         bias, act, out, ldo, out_f32);
+  return check_launch(err);
+}
+
+int broadcast_row_launch(const __nv_bfloat16* src, int dim, int rows, __nv_bfloat16* dst, cudaStream_t s,
+                         const char** err) {
+  const long long total = static_cast<long long>(rows) * (dim >> 3);
+  broadcast_row_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(src, dim, rows, dst);
   return check_launch(err);
 }
 

@@ -86,6 +86,10 @@ int head_out_launch(const __nv_bfloat16* x, int rows, const float* ln_w, const f
 // Pro-variant RoPE table (action_heads.py:150-164): angle(t, j) = t * inv_freq[j mod 56], hd = 112.
 int policy_rope_table_launch(float* cos_t, float* sin_t, int max_pos, cudaStream_t s, const char** err);
 
+// dst[r, :] = src[:] for r in [0, rows)  (the input-independent MLPResNet prologue x0, AH:114-116)
+int broadcast_row_launch(const __nv_bfloat16* src, int dim, int rows, __nv_bfloat16* dst, cudaStream_t s,
+                         const char** err);
+
 // Copies rows [r0, r0+rows) of every slab into a dense buffer (tap extraction).
 int gather_rows_launch(const __nv_bfloat16* src, long long src_bs, int ld, int r0, int rows, int batches,
                        int dim, __nv_bfloat16* dst, cudaStream_t s, const char** err);
