@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py - action chunks/sec of the batched predict_action path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our engine, N ranks x B samples (weak scaling)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A step is one pass of the hot path over one batch of synthetic LIBERO-shaped observations
+(2 x 224px images, prompt of 48 tokens, 64 ActionQuery tokens, proprio, 8x7 chunk; BASELINE.json configs[2]).
+One JSON line is printed by rank 0.  `value` is device-resident throughput (inputs already in HBM), `e2e`
+goes through the host-buffer C-ABI call (H2D of the observations and D2H of the chunks inside the timed
+region), `roofline` describes the dominant kernel (the tcgen05 GEMM) and `cpu_baseline` is the CPU oracle
+timed on this box's cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "action_chunks_per_sec"
+UNIT = "chunks/s"
+PROMPT_LEN = 48
+N_IMAGES = 2
+T_CHUNK, A_DIM, P_DIM = 8, 7, 8
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tflops_sustained": d.get("bf16_tflops_sustained"), "tflops_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def algorithmic_gflop(n_images: int, L: int, T: int, A: int):
+    """Algorithmic FLOPs per sample: what a correct implementation must do.  Excludes the
+    discarded last ViT blocks, lm_head, the non-causal half of attention, AQ63/stop rows."""
+    def vit(D, Fh, blocks, S):
+        lin = S * 2 * (4 * D * D + 2 * D * Fh)
+        att = 4 * S * S * D
+        return blocks * lin + 2 * 256 * 588 * D, blocks * att
+    dl, da = vit(1024, 4096, 23, 261)
+    sl, sa = vit(1152, 4304, 26, 256)
+    proj = 2 * 256 * (2176 * 8704 + 8704 * 896 + 896 * 896)
+    NP = 256 * n_images
+    S = NP + L + 63
+    llm_lin = 24 * 2 * S * 14909440
+    llm_att = 24 * 2 * S * S * 896
+    ctx = T + 65 + NP
+    pol_lin = 24 * 2 * 896 * 896 * (3 * T + 2 * ctx) + 2 * T * 896 * A
+    pol_att = 24 * 4 * T * ctx * 896
+    gemm = n_images * (dl + sl + proj) + llm_lin + pol_lin
+    att = n_images * (da + sa) + llm_att + pol_att
+    return {"total": (gemm + att) / 1e9, "gemm": gemm / 1e9, "attention": att / 1e9}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_inputs(B: int, L: int, seed: int, device):
+    """Distinct synthetic observations per sample: uint8 images through the processor's two normalisations
+    (preprocessor_config.json), random prompt ids, clipped proprio."""
+    g = torch.Generator(device=device).manual_seed(1234 + seed)
+    img = torch.randint(0, 256, (B, N_IMAGES, 3, 224, 224), generator=g, device=device).float() / 255.0
+    m0 = torch.tensor([0.485, 0.456, 0.406], device=device).view(1, 1, 3, 1, 1)
+    s0 = torch.tensor([0.229, 0.224, 0.225], device=device).view(1, 1, 3, 1, 1)
+    pix = torch.cat([(img - m0) / s0, (img - 0.5) / 0.5], dim=2).reshape(B, 6 * N_IMAGES, 224, 224)
+    ids = torch.randint(3, 151643, (B, L), generator=g, device=device, dtype=torch.int64)
+    prop = torch.randn(B, P_DIM, generator=g, device=device).clamp(-1, 1)
+    return pix.to(torch.bfloat16).contiguous(), ids, prop.float().contiguous()
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm (oracle port, bf16 like the reference requires) on all host
+    cores.  Each step is a bounded sample of the step's batch: ONE observation (1/B of the batch)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import vla_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.OracleConfig(n_images=N_IMAGES, pro=args.variant == "pro", chunk_len=T_CHUNK, action_dim=A_DIM,
+                         proprio_dim=P_DIM)
+    W = O.make_weights(cfg, seed=0)
+    pix, ids, prop = O.make_inputs(cfg, 1, PROMPT_LEN, seed=0)
+    budget_s = args.ref_budget
+    times = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.predict_action_batch(W, cfg, pix, ids, prop, torch.bfloat16)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+        # keep the whole run bounded: once the budget is spent, stop (steps actually timed are reported)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 1:
+            break
+    ms = statistics.mean(times) * 1e3
+    val = 1000.0 / ms
+    sample = (f"1 observation per step (1/{args.batch} of the bs={args.batch} batch), bf16 torch-CPU oracle, "
+              f"{len(times)} timed steps of the requested {args.steps}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"LIBERO predict_action bs={args.batch} (configs[2]); reference arm samples 1 observation/step",
+                   "n_images": N_IMAGES, "prompt_len": PROMPT_LEN, "chunk": [T_CHUNK, A_DIM], "variant": args.variant},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
+    ap.add_argument("--variant", default="base", choices=["base", "pro"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=200.0, help="wall-clock bound [s] of the reference arm")
+    ap.add_argument("--latency-iters", type=int, default=30)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from vla_adapter_b200 import _lib
+    from vla_adapter_b200.engine import VLAEngine
+    from vla_adapter_b200.weights import load_random_weights
+    from vla_adapter_b200 import tokens
+
+    B, L, K, Wu = args.batch, PROMPT_LEN, args.steps, args.warmup
+    pro = args.variant == "pro"
+    eng = VLAEngine(n_images=N_IMAGES, chunk_len=T_CHUNK, action_dim=A_DIM, proprio_dim=P_DIM, pro=pro, max_batch=B,
+                    max_prompt_len=L, device=local,
+                    norm_stats={"synthetic": {"action": {"q01": [-1.0] * A_DIM, "q99": [1.0] * A_DIM,
+                                                         "mask": [True] * 6 + [False]}}})
+    n_params = load_random_weights(eng, seed=0, n_images=N_IMAGES, action_dim=A_DIM, proprio_dim=P_DIM, pro=pro)
+    eng.finalize()
+    lib = _lib.load()
+
+    pix, ids, prop = synth_inputs(B, L, seed=rank, device=dev)
+    ext, _, _, aq, _ = tokens.build(ids.cpu(), None, A_DIM)
+    ext_d, aq_d = ext.to(dev), aq.to(dev)
+    gathered = torch.empty((world * B, T_CHUNK, A_DIM), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step_device():
+        out_n, out_u, _ = eng.predict_device(pix, ext_d, aq_d, prop)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_u)  # the only collective: action chunks over NVLink
+        return out_u
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput
+    for _ in range(Wu):
+        step_device()
+    sync_all()
+    launches0 = lib.vla_total_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(K):
+            out = step_device()
+        e1.record()
+        sync_all()
+    ms_step = reduce_max(e0.elapsed_time(e1) / K)
+    launches = lib.vla_total_launch_count() - launches0
+    value = world * B / (ms_step * 1e-3)
+    assert torch.isfinite(out).all(), "non-finite action chunk"
+
+    # ---------------- end to end through the host-buffer C-ABI call (pinned host memory)
+    pix_h, ext_h, aq_h, prop_h = pix.cpu().pin_memory(), ext.pin_memory(), aq.pin_memory(), prop.cpu().pin_memory()
+    on_h = torch.empty((B, T_CHUNK, A_DIM), dtype=torch.float32).pin_memory()
+    ou_h = torch.empty((B, T_CHUNK, A_DIM), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        eng.predict_host(pix_h, ext_h, aq_h, prop_h, on_h, ou_h)
+    sync_all()
+    e0.record()
+    for _ in range(K):
+        eng.predict_host(pix_h, ext_h, aq_h, prop_h, on_h, ou_h)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, ou_h.to(dev, non_blocking=True))
+    e1.record()
+    sync_all()
+    ms_e2e = reduce_max(e0.elapsed_time(e1) / K)
+    h2d = pix_h.numel() * 2 + ext_h.numel() * 8 + aq_h.numel() * 4 + prop_h.numel() * 4
+    d2h = 2 * on_h.numel() * 4 + 4
+    assert torch.equal(ou_h, out.cpu()), "host-path result differs from device-path result"
+
+    # ---------------- roofline of the dominant kernel: tcgen05 GEMM, timed per launch with CUDA events
+    lib.vla_profile_gemm(1)
+    step_device()
+    torch.cuda.synchronize()
+    import ctypes as C
+    g_ms, g_n = C.c_double(0), C.c_longlong(0)
+    lib.vla_profile_gemm_read(C.byref(g_ms), C.byref(g_n))
+    lib.vla_profile_gemm(0)
+    peaks = measured_peaks()
+    alg = algorithmic_gflop(N_IMAGES, L, T_CHUNK, A_DIM)
+    gemm_tflops = alg["gemm"] * B / g_ms.value  # GFLOP / ms = TFLOP/s
+    peak = peaks["tflops_sustained"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": gemm_tflops, "peak": peak,
+                "unit": "TFLOP/s", "frac": gemm_tflops / peak, "traffic": traffic,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_per_step": int(g_n.value), "avg_launch_ms": g_ms.value / max(1, g_n.value),
+                "gemm_ms_per_step": g_ms.value, "gemm_share_of_step": g_ms.value / ms_step,
+                "algorithmic_gflop_per_sample": alg}
+    step_tflops = alg["total"] * B / ms_step
+    step_roofline = {"achieved": step_tflops, "peak": peak, "unit": "TFLOP/s", "frac": step_tflops / peak,
+                     "note": "whole step (all kernels) against the same measured dense-bf16 peak"}
+
+    # ---------------- bs=1 latency through the host path (p50 / p90), BASELINE.json's second metric
+    lat = []
+    one = [t[:1].contiguous().pin_memory() for t in (pix_h, ext_h, aq_h, prop_h)]
+    o1, o2 = on_h[:1].clone().pin_memory(), ou_h[:1].clone().pin_memory()
+    for i in range(args.latency_iters + 5):
+        t0 = time.perf_counter()
+        eng.predict_host(one[0], one[1], one[2], one[3], o1, o2)
+        if i >= 5:
+            lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    latency = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "iters": len(lat),
+               "how": "wall clock around vla_predict_host(B=1) incl. H2D/D2H and stream sync"}
+
+    # ---------------- CPU baseline (rank 0, N=1 only): the oracle on this box's cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import vla_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ocfg = O.OracleConfig(n_images=N_IMAGES, pro=pro, chunk_len=T_CHUNK, action_dim=A_DIM, proprio_dim=P_DIM,
+                              vocab_size=4096)
+        OW = O.make_weights(ocfg, seed=0)
+        opix, oids, oprop = O.make_inputs(ocfg, 1, L, seed=0)
+        O.predict_action_batch(OW, ocfg, opix, oids, oprop, torch.bfloat16)  # warm-up (oneDNN primitive caches)
+        dts = []
+        t_begin = time.perf_counter()
+        while len(dts) < 5 and (time.perf_counter() - t_begin < 20.0 or not dts):
+            t0 = time.perf_counter()
+            O.predict_action_batch(OW, ocfg, opix, oids, oprop, torch.bfloat16)
+            dts.append(time.perf_counter() - t0)
+        dt = statistics.median(dts)
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "1 observation per call (1/%d of the batch), bf16 torch-CPU oracle, median of %d calls after "
+                         "1 warm-up, embedding table cut to 4096 rows (gather only)" % (B, len(dts))}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"LIBERO predict_action bs={B}/GPU (BASELINE.json configs[2]): 2x224px images, "
+                                   f"L={L} prompt, 64 ActionQuery, proprio, {T_CHUNK}x{A_DIM} chunk, {args.variant} head",
+                       "global_batch": world * B, "per_gpu_batch": B, "params": n_params,
+                       "parallelism": f"sample-sharded x{world}, full weight replica per GPU, all-gather of chunks",
+                       "l2": "no explicit flush: per-step working set (2.7 GB weights + >4 GB activations) >> 126 MB L2"},
+            "clocks": clk.summary(),
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "step_roofline": step_roofline, "latency_bs1": latency,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

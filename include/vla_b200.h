@@ -152,6 +152,13 @@ int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_of
  * of each row; position = row % S. */
 int vla_op_rope(void* x, int ld, int off, int n_heads, int B, int S, float theta, void* stream);
 
+/* Per-launch CUDA-event timing of the tcgen05 GEMM kernel, for bench.py's roofline object: after
+ * vla_profile_gemm(1) every GEMM launch is bracketed by events on its own stream;
+ * vla_profile_gemm_read() synchronises them, returns the summed kernel time [ms] and the number of
+ * launches since the last read, and clears the records. */
+int vla_profile_gemm(int enable);
+int vla_profile_gemm_read(double* total_ms, long long* launches);
+
 const char* vla_global_error(void);
 long long vla_total_launch_count(void);
 

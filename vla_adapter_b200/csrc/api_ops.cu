@@ -19,6 +19,15 @@ const char* vla_global_error(void) { return g_err.c_str(); }
 
 long long vla_total_launch_count(void) { return vla::gemm_launch_count() + vla::ops_launch_count(); }
 
+int vla_profile_gemm(int enable) {
+  vla::gemm_profile_enable(enable != 0);
+  return 0;
+}
+
+int vla_profile_gemm_read(double* total_ms, long long* launches) {
+  return vla::gemm_profile_read(total_ms, launches);
+}
+
 int vla_op_gemm(const void* A, long long a_batch_stride, int lda, int rows, int batches, const void* W,
                 int ldw, int N, int K, void* C, long long c_batch_stride, int ldc, const float* bias,
                 const float* colscale, const void* resid, long long r_batch_stride, int ldr, int act,

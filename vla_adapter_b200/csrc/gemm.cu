@@ -19,6 +19,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace vla {
 
@@ -303,6 +304,15 @@ bool make_map_3d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows
 
 std::atomic<long long> g_launches{0};
 
+// Optional per-launch timing (bench.py's roofline leg): cudaEvents recorded around every GEMM launch on
+// the launching stream.  Off by default; never used under graph capture.
+struct ProfRec {
+  cudaEvent_t e0, e1;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -329,7 +339,19 @@ int launch_bn(const CUtensorMap& mA, const CUtensorMap& mB, const GemmDev& p, cu
   }
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < num_sms() ? total : num_sms();
+  ProfRec rec{};
+  const bool prof = g_prof_on;
+  if (prof) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    cudaEventRecord(rec.e0, stream);
+  }
   gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mA, mB, p);
+  if (prof) {
+    cudaEventRecord(rec.e1, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = cudaGetErrorString(e);
@@ -342,6 +364,28 @@ int launch_bn(const CUtensorMap& mA, const CUtensorMap& mB, const GemmDev& p, cu
 }  // namespace
 
 long long gemm_launch_count() { return g_launches.load(); }
+
+void gemm_profile_enable(bool on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on;
+}
+
+// Synchronises the recorded events, returns the summed GEMM kernel time and clears the records.
+int gemm_profile_read(double* total_ms, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double tot = 0.0;
+  for (auto& r : g_prof) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) tot += ms;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = static_cast<long long>(g_prof.size());
+  g_prof.clear();
+  return 0;
+}
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   if (!a.A || !a.W || !a.C || a.rows <= 0 || a.batches <= 0 || a.N <= 0 || a.K <= 0) {

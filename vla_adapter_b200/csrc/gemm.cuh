@@ -46,4 +46,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err);
 // Number of GEMM kernel launches issued since process start (for bench.py's gpu_launches).
 long long gemm_launch_count();
 
+// Per-launch CUDA-event timing of the GEMM kernel (bench.py roofline leg).
+void gemm_profile_enable(bool on);
+int gemm_profile_read(double* total_ms, long long* launches);
+
 }  // namespace vla
