@@ -308,14 +308,16 @@ def main():
     lat = []
     one = [t[:1].contiguous().pin_memory() for t in (pix_h, ext_h, aq_h, prop_h)]
     o1, o2 = on_h[:1].clone().pin_memory(), ou_h[:1].clone().pin_memory()
-    for i in range(args.latency_iters + 5):
+    for i in range(args.latency_iters + 5 if args.latency_iters > 0 else 0):
         t0 = time.perf_counter()
         eng.predict_host(one[0], one[1], one[2], one[3], o1, o2)
         if i >= 5:
             lat.append((time.perf_counter() - t0) * 1e3)
     lat.sort()
-    latency = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "iters": len(lat),
-               "how": "wall clock around vla_predict_host(B=1) incl. H2D/D2H and stream sync"}
+    latency = None
+    if lat:
+        latency = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "iters": len(lat),
+                   "how": "wall clock around vla_predict_host(B=1) incl. H2D/D2H and stream sync"}
 
     # ---------------- CPU baseline (rank 0, N=1 only): the oracle on this box's cores, bounded sample
     cpu = None

@@ -18,6 +18,8 @@
 #include "gemm.cuh"
 
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -308,7 +310,9 @@ std::atomic<long long> g_launches{0};
 // the launching stream.  Off by default; never used under graph capture.
 struct ProfRec {
   cudaEvent_t e0, e1;
+  int rows, batches, N, K, bn, act;
 };
+FILE* g_prof_csv = nullptr;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 std::mutex g_prof_mu;
@@ -340,6 +344,7 @@ int launch_bn(const CUtensorMap& mA, const CUtensorMap& mB, const GemmDev& p, cu
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < num_sms() ? total : num_sms();
   ProfRec rec{};
+  rec.rows = p.rows; rec.batches = p.batches; rec.N = p.N; rec.K = p.K; rec.bn = BN; rec.act = p.act;
   const bool prof = g_prof_on;
   if (prof) {
     cudaEventCreate(&rec.e0);
@@ -368,6 +373,11 @@ long long gemm_launch_count() { return g_launches.load(); }
 void gemm_profile_enable(bool on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = on;
+  // Optional per-launch CSV (rows,batches,N,K,bn,act,ms,TFLOP/s) for tuning: VLA_GEMM_PROF_CSV=<path>
+  const char* path = getenv("VLA_GEMM_PROF_CSV");
+  if (on && path && !g_prof_csv) {
+    g_prof_csv = fopen(path, "a");
+  }
 }
 
 // Synchronises the recorded events, returns the summed GEMM kernel time and clears the records.
@@ -378,12 +388,18 @@ int gemm_profile_read(double* total_ms, long long* launches) {
     cudaEventSynchronize(r.e1);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) tot += ms;
+    if (g_prof_csv) {
+      const double fl = 2.0 * r.rows * r.batches * r.N * r.K;
+      fprintf(g_prof_csv, "%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.rows, r.batches, r.N, r.K, r.bn, r.act, ms,
+              fl / (ms * 1e-3) / 1e12);
+    }
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }
   if (total_ms) *total_ms = tot;
   if (launches) *launches = static_cast<long long>(g_prof.size());
   g_prof.clear();
+  if (g_prof_csv) fflush(g_prof_csv);
   return 0;
 }
 
