@@ -46,8 +46,9 @@ VLA_DEVINL void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, u
 
 template <int HD, int HDP>
 __global__ void __launch_bounds__(ATT_THREADS)
-flash_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int S,
-                  int group, int causal, float scale_log2, __nv_bfloat16* __restrict__ out, int ld_out) {
+flash_attn_kernel(const __nv_bfloat16* __restrict__ qp, int ld_q, int Sq, const __nv_bfloat16* __restrict__ kp,
+                  const __nv_bfloat16* __restrict__ vp, int ld, int S, int group, int causal, float scale_log2,
+                  __nv_bfloat16* __restrict__ out, int ld_out) {
   constexpr int LDS = HDP + 8;          // smem row stride (elements): odd multiple of 16 B
   constexpr int CH = HD / 8;            // 16-byte chunks per global row
   constexpr int KSTEPS = HDP / 16;      // k-steps of QK^T
@@ -60,10 +61,12 @@ flash_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int q_off, int 
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / group;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // q rows: [b*Sq, (b+1)*Sq) of qp; k/v rows: [b*S, (b+1)*S) of kp/vp (self-attention passes Sq == S)
+  const long long q_base = static_cast<long long>(b) * Sq;
   const long long row_base = static_cast<long long>(b) * S;
-  const __nv_bfloat16* gq = qkv + row_base * ld + q_off + h * HD;
-  const __nv_bfloat16* gk = qkv + row_base * ld + k_off + kvh * HD;
-  const __nv_bfloat16* gv = qkv + row_base * ld + v_off + kvh * HD;
+  const __nv_bfloat16* gq = qp + q_base * ld_q + h * HD;
+  const __nv_bfloat16* gk = kp + row_base * ld + kvh * HD;
+  const __nv_bfloat16* gv = vp + row_base * ld + kvh * HD;
 
   // zero the pad columns once (cp.async never writes them)
   if (HDP > HD) {
@@ -78,8 +81,8 @@ flash_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int q_off, int 
   const int q0 = qb * ATT_BM;
   for (int i = tid; i < ATT_BM * CH; i += ATT_THREADS) {
     const int r = i / CH, c = i % CH;
-    const bool ok = (q0 + r) < S;
-    cp_async16(smem_u32(sQ + r * LDS + c * 8), gq + static_cast<long long>(ok ? q0 + r : 0) * ld + c * 8, ok);
+    const bool ok = (q0 + r) < Sq;
+    cp_async16(smem_u32(sQ + r * LDS + c * 8), gq + static_cast<long long>(ok ? q0 + r : 0) * ld_q + c * 8, ok);
   }
   auto load_kv = [&](int it, int buf) {
     const int k0 = it * ATT_BN;
@@ -211,15 +214,15 @@ flash_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int q_off, int 
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
   }
   const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
-  __nv_bfloat16* go = out + row_base * ld_out + h * HD;
+  __nv_bfloat16* go = out + q_base * ld_out + h * HD;
 #pragma unroll
   for (int nb = 0; nb < ONB; ++nb) {
     const int col = nb * 8 + t * 2;
     if (col < HD) {
-      if (qrow0 < S)
+      if (qrow0 < Sq)
         *reinterpret_cast<uint32_t*>(go + static_cast<long long>(qrow0) * ld_out + col) =
             pack_bf16(o[nb][0] * inv0, o[nb][1] * inv0);
-      if (qrow0 + 8 < S)
+      if (qrow0 + 8 < Sq)
         *reinterpret_cast<uint32_t*>(go + static_cast<long long>(qrow0 + 8) * ld_out + col) =
             pack_bf16(o[nb][2] * inv1, o[nb][3] * inv1);
     }
@@ -227,8 +230,9 @@ flash_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int q_off, int 
 }
 
 template <int HD, int HDP>
-int launch_attn(const __nv_bfloat16* qkv, int ld, int q_off, int k_off, int v_off, int B, int S, int n_heads,
-                int group, int causal, __nv_bfloat16* out, int ld_out, cudaStream_t s, const char** err) {
+int launch_attn(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ld,
+                int B, int S, int n_heads, int group, int causal, __nv_bfloat16* out, int ld_out, cudaStream_t s,
+                const char** err) {
   constexpr int LDS = HDP + 8;
   constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * LDS * 2;
   static bool attr_set = false;
@@ -241,9 +245,9 @@ int launch_attn(const __nv_bfloat16* qkv, int ld, int q_off, int k_off, int v_of
     attr_set = true;
   }
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * 1.4426950408889634f;
-  dim3 grid((S + ATT_BM - 1) / ATT_BM, n_heads, B);
-  flash_attn_kernel<HD, HDP><<<grid, ATT_THREADS, SMEM, s>>>(qkv, ld, q_off, k_off, v_off, S, group, causal,
-                                                            scale_log2, out, ld_out);
+  dim3 grid((Sq + ATT_BM - 1) / ATT_BM, n_heads, B);
+  flash_attn_kernel<HD, HDP><<<grid, ATT_THREADS, SMEM, s>>>(q, ld_q, Sq, k, v, ld, S, group, causal, scale_log2,
+                                                            out, ld_out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = cudaGetErrorString(e);
@@ -263,13 +267,27 @@ int attention_launch(const __nv_bfloat16* qkv, int ld_qkv, int q_off, int k_off,
     if (err) *err = "attention: offsets/strides must be multiples of 8 elements";
     return -1;
   }
-  if (hd == 64)
-    return launch_attn<64, 64>(qkv, ld_qkv, q_off, k_off, v_off, B, S, n_heads, group, causal, out, ld_out, s,
-                               err);
-  if (hd == 72)
-    return launch_attn<72, 80>(qkv, ld_qkv, q_off, k_off, v_off, B, S, n_heads, group, causal, out, ld_out, s,
-                               err);
-  if (err) *err = "attention: head dim must be 64 or 72";
+  return cross_attention_launch(qkv + q_off, ld_qkv, S, qkv + k_off, qkv + v_off, ld_qkv, S, B, n_heads, group, hd,
+                                causal, out, ld_out, s, err);
+}
+
+int cross_attention_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                           int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal,
+                           __nv_bfloat16* out, int ld_out, cudaStream_t s, const char** err) {
+  if ((ld_q & 7) || (ld_kv & 7) || (ld_out & 1) || group <= 0 || (n_heads % group) ||
+      (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
+      (reinterpret_cast<uintptr_t>(v) & 15)) {
+    if (err) *err = "attention: strides must be multiples of 8 elements and pointers 16-byte aligned";
+    return -1;
+  }
+  if (causal && Sq != Skv) {
+    if (err) *err = "attention: causal masking needs Sq == Skv";
+    return -1;
+  }
+  if (hd == 64) return launch_attn<64, 64>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, causal, out, ld_out, s, err);
+  if (hd == 72) return launch_attn<72, 80>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, causal, out, ld_out, s, err);
+  if (hd == 112) return launch_attn<112, 112>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, causal, out, ld_out, s, err);
+  if (err) *err = "attention: head dim must be 64, 72 or 112";
   return -1;
 }
 

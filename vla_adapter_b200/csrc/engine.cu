@@ -54,8 +54,9 @@ struct LlmLayer {
   bf16 *wqkv, *wo, *wgu, *wdown;
 };
 struct HeadBlock {
-  bf16 *wqkv_self, *wkv_cond, *wkv_vis, *wo, *wffn;
-  float *bqkv_self, *bkv_cond, *bkv_vis, *bo, *ffn_lnw, *ffn_lnb, *bffn;
+  bf16 *wq, *wkv_self, *wkv_cond, *wkv_vis, *wo, *wffn;
+  float *bq, *bkv_self, *bkv_cond, *bkv_vis, *bo, *ffn_lnw, *ffn_lnb, *bffn;
+  float* gatevec;  // [1792]: tanh(gating_factor) on the K half, 1 on the V half (epilogue column scale)
   float gate;
 };
 
@@ -97,8 +98,8 @@ struct vla_engine {
   float *rope_cos = nullptr, *rope_sin = nullptr;
   // head
   std::vector<HeadBlock> head;
-  bf16 *x0, *wkv_p_all, *head_fc2_w, *pp_w1, *pp_w2;
-  float *bkv_p_all, *head_ln2w, *head_ln2b, *head_fc2_b, *pp_b1, *pp_b2;
+  bf16 *x0, *head_fc2_w, *pp_w1, *pp_w2;
+  float *head_ln2w, *head_ln2b, *head_fc2_b, *pp_b1, *pp_b2;
   float *prope_cos = nullptr, *prope_sin = nullptr;
   float *st_hi = nullptr, *st_lo = nullptr;
   uint8_t* st_mask = nullptr;
@@ -109,7 +110,7 @@ struct vla_engine {
   bf16 *w_col, *w_x, *w_xn, *w_qkv, *w_attn, *w_h, *w_patches, *w_ph1, *w_ph2;
   std::vector<bf16*> hid;  // 25 LLM states
   bf16 *l_tmp, *l_xn, *l_qkv, *l_attn, *l_act;
-  bf16 *h_p1, *h_p, *h_pkv, *h_kva, *h_kvt, *h_qkv, *h_ao, *h_y, *h_yn;
+  bf16 *h_p1, *h_p, *h_kv, *h_q, *h_ao, *h_y, *h_yn;
   std::vector<bf16*> head_x;  // 25 policy states
   int* err_flag = nullptr;
   // pinned/dev staging for vla_predict_host
@@ -358,36 +359,46 @@ int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_
   CK(vla::skinny_linear_launch(proprio, 1, P, B, P, e->pp_w1, P, D_LLM, e->pp_b1, 1, e->h_p1, D_LLM, nullptr, s, &_err));
   CK(vla::skinny_linear_launch(e->h_p1, 0, D_LLM, B, D_LLM, e->pp_w2, D_LLM, D_LLM, e->pp_b2, 0, e->h_p, D_LLM, nullptr, s, &_err));
   const int NB = static_cast<int>(e->head.size());
-  {
-    vla::GemmArgs g;
-    g.A = e->h_p; g.lda = D_LLM; g.rows = B; g.W = e->wkv_p_all; g.ldw = D_LLM; g.N = NB * PKV; g.K = D_LLM;
-    g.C = e->h_pkv; g.ldc = NB * PKV; g.bias = e->bkv_p_all;
-    CK(vla::gemm_launch(g, s, &_err));
-  }
   CK(vla::broadcast_row_launch(e->x0, D_LLM, B * T, e->head_x[0], s, &_err));
   const int ha_row0 = NP + L - 1;  // MP:855 with NUM_PROMPT_TOKENS = L-1 (MP:927)
+  const int NK = T + N_AQ + 1 + NP;  // keys per sample: self | h_a ++ p | h_t
+  const long long kv_bs = static_cast<long long>(NK) * PKV;
+  const bool pro = e->cfg.variant == VLA_HEAD_PRO;
   for (int i = 0; i < NB; ++i) {
     const HeadBlock& w = e->head[i];
     const bf16* hs = e->hid[i + 1];  // AH:118: block i reads hidden state i+1
+    // K|V of the 64 ActionQuery rows -> kv rows [T, T+64)
     vla::GemmArgs g;
     g.A = hs + static_cast<long long>(ha_row0) * D_LLM; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM;
     g.rows = N_AQ; g.batches = B; g.W = w.wkv_cond; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
-    g.C = e->h_kva; g.c_batch_stride = static_cast<long long>(N_AQ) * PKV; g.ldc = PKV; g.bias = w.bkv_cond;
+    g.C = e->h_kv + static_cast<long long>(T) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_cond;
     CK(vla::gemm_launch(g, s, &_err));
+    // K|V of the proprio row -> kv row T+64
+    g = vla::GemmArgs();
+    g.A = e->h_p; g.a_batch_stride = D_LLM; g.lda = D_LLM; g.rows = 1; g.batches = B;
+    g.W = w.wkv_cond; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
+    g.C = e->h_kv + static_cast<long long>(T + N_AQ) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_cond;
+    CK(vla::gemm_launch(g, s, &_err));
+    // K|V of the NP raw rows -> kv rows [T+65, NK); K columns scaled by tanh(gating_factor) (AH:269 / AH:391)
     g = vla::GemmArgs();
     g.A = hs; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM; g.rows = NP; g.batches = B;
     g.W = w.wkv_vis; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
-    g.C = e->h_kvt; g.c_batch_stride = static_cast<long long>(NP) * PKV; g.ldc = PKV; g.bias = w.bkv_vis;
+    g.C = e->h_kv + static_cast<long long>(T + N_AQ + 1) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV;
+    g.bias = w.bkv_vis; g.colscale = w.gatevec;
+    CK(vla::gemm_launch(g, s, &_err));
+    // q and self K|V of the current x -> kv rows [0, T)
+    g = vla::GemmArgs();
+    g.A = e->head_x[i]; g.lda = D_LLM; g.rows = B * T; g.W = w.wq; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
+    g.C = e->h_q; g.ldc = D_LLM; g.bias = w.bq;
     CK(vla::gemm_launch(g, s, &_err));
     g = vla::GemmArgs();
-    g.A = e->head_x[i]; g.lda = D_LLM; g.rows = B * T; g.W = w.wqkv_self; g.ldw = D_LLM; g.N = 3 * D_LLM; g.K = D_LLM;
-    g.C = e->h_qkv; g.ldc = 3 * D_LLM; g.bias = w.bqkv_self;
+    g.A = e->head_x[i]; g.a_batch_stride = static_cast<long long>(T) * D_LLM; g.lda = D_LLM; g.rows = T; g.batches = B;
+    g.W = w.wkv_self; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
+    g.C = e->h_kv; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_self;
     CK(vla::gemm_launch(g, s, &_err));
-    vla::PolicyAttnArgs pa;
-    pa.qkv_self = e->h_qkv; pa.kv_a = e->h_kva; pa.kv_p = e->h_pkv + static_cast<long long>(i) * PKV; pa.ld_p = NB * PKV;
-    pa.kv_t = e->h_kvt; pa.B = B; pa.T = T; pa.NP = NP; pa.gate = w.gate; pa.pro = e->cfg.variant == VLA_HEAD_PRO;
-    pa.rope_cos = e->prope_cos; pa.rope_sin = e->prope_sin; pa.out = e->h_ao;
-    CK(vla::policy_attention_launch(pa, s, &_err));
+    if (pro) CK(vla::policy_rope_launch(e->h_q, e->h_kv, B, T, NP, e->prope_cos, e->prope_sin, s, &_err));
+    CK(vla::cross_attention_launch(e->h_q, D_LLM, T, e->h_kv, e->h_kv + D_LLM, PKV, NK, B, 8, 1, 112, 0, e->h_ao,
+                                   D_LLM, s, &_err));
     g = vla::GemmArgs();
     g.A = e->h_ao; g.lda = D_LLM; g.rows = B * T; g.W = w.wo; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
     g.C = e->h_y; g.ldc = D_LLM; g.bias = w.bo; g.resid = e->head_x[i]; g.ldr = D_LLM;
@@ -568,16 +579,18 @@ int vla_finalize(vla_engine* e) {
       const std::string ks = pro ? "k_self" : "k_proj", vs = pro ? "v_self" : "v_proj";
       const std::string kc = pro ? "k_adapter" : "k_proj", vc = pro ? "v_adapter" : "v_proj";
       const std::string kv = pro ? "k_task" : "k_proj", vv = pro ? "v_task" : "v_proj";
-      w.wqkv_self = e->pack_cat({{b + "q_proj.weight", D_LLM}, {b + ks + ".weight", D_LLM}, {b + vs + ".weight", D_LLM}}, D_LLM);
-      w.bqkv_self = e->cat_f32({{b + "q_proj.bias", D_LLM}, {b + ks + ".bias", D_LLM}, {b + vs + ".bias", D_LLM}});
+      w.wq = e->pack(b + "q_proj.weight", D_LLM, D_LLM);
+      w.bq = e->f32(b + "q_proj.bias", D_LLM);
       w.wkv_cond = e->pack_cat({{b + kc + ".weight", D_LLM}, {b + vc + ".weight", D_LLM}}, D_LLM);
       w.bkv_cond = e->cat_f32({{b + kc + ".bias", D_LLM}, {b + vc + ".bias", D_LLM}});
       if (pro) {
+        w.wkv_self = e->pack_cat({{b + ks + ".weight", D_LLM}, {b + vs + ".weight", D_LLM}}, D_LLM);
+        w.bkv_self = e->cat_f32({{b + ks + ".bias", D_LLM}, {b + vs + ".bias", D_LLM}});
         w.wkv_vis = e->pack_cat({{b + kv + ".weight", D_LLM}, {b + vv + ".weight", D_LLM}}, D_LLM);
         w.bkv_vis = e->cat_f32({{b + kv + ".bias", D_LLM}, {b + vv + ".bias", D_LLM}});
-      } else {
-        w.wkv_vis = w.wkv_cond;
-        w.bkv_vis = w.bkv_cond;
+      } else {  // base: one shared k_proj / v_proj for all three segments (AH:247-254)
+        w.wkv_self = w.wkv_vis = w.wkv_cond;
+        w.bkv_self = w.bkv_vis = w.bkv_cond;
       }
       w.wo = e->pack(b + "o_proj.weight", D_LLM, D_LLM);
       w.bo = e->f32(b + "o_proj.bias", D_LLM);
@@ -590,14 +603,14 @@ int vla_finalize(vla_engine* e) {
       // ratio_g = tanh(g) evaluated in the parameter dtype (bf16), AH:225 / AH:344
       const float gb = __bfloat162float(__float2bfloat16_rn(g));
       w.gate = __bfloat162float(__float2bfloat16_rn(std::tanh(gb)));
-      pw.push_back({b + kc + ".weight", D_LLM});
-      pw.push_back({b + vc + ".weight", D_LLM});
-      pb.push_back({b + kc + ".bias", D_LLM});
-      pb.push_back({b + vc + ".bias", D_LLM});
+      {
+        std::vector<float> gv(PKV, 1.0f);
+        for (int c2 = 0; c2 < D_LLM; ++c2) gv[c2] = w.gate;
+        w.gatevec = e->dalloc<float>(PKV);
+        cudaMemcpy(w.gatevec, gv.data(), PKV * sizeof(float), cudaMemcpyHostToDevice);
+      }
       e->head.push_back(w);
     }
-    e->wkv_p_all = e->pack_cat(pw, D_LLM);
-    e->bkv_p_all = e->cat_f32(pb);
     e->head_ln2w = e->f32(hm + "layer_norm2.weight", D_LLM);
     e->head_ln2b = e->f32(hm + "layer_norm2.bias", D_LLM);
     e->head_fc2_w = e->pack(hm + "fc2.weight", e->A, D_LLM);
@@ -642,10 +655,8 @@ int vla_finalize(vla_engine* e) {
     const size_t BT = static_cast<size_t>(B) * e->T;
     e->h_p1 = e->dalloc<bf16>(static_cast<size_t>(B) * D_LLM);
     e->h_p = e->dalloc<bf16>(static_cast<size_t>(B) * D_LLM);
-    e->h_pkv = e->dalloc<bf16>(static_cast<size_t>(B) * 24 * PKV);
-    e->h_kva = e->dalloc<bf16>(static_cast<size_t>(B) * N_AQ * PKV);
-    e->h_kvt = e->dalloc<bf16>(static_cast<size_t>(B) * e->NP * PKV);
-    e->h_qkv = e->dalloc<bf16>(BT * 3 * D_LLM);
+    e->h_kv = e->dalloc<bf16>(static_cast<size_t>(B) * (e->T + N_AQ + 1 + e->NP) * PKV);
+    e->h_q = e->dalloc<bf16>(BT * D_LLM);
     e->h_ao = e->dalloc<bf16>(BT * D_LLM);
     e->h_y = e->dalloc<bf16>(BT * D_LLM);
     e->h_yn = e->dalloc<bf16>(BT * D_LLM);

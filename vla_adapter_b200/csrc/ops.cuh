@@ -35,6 +35,13 @@ int attention_launch(const __nv_bfloat16* qkv, int ld_qkv, int q_off, int k_off,
                      int n_heads, int group, int hd, int causal, __nv_bfloat16* out, int ld_out,
                      cudaStream_t s, const char** err);
 
+// General form: q rows [b*Sq, (b+1)*Sq) of `q` (head h at column h*hd), k/v rows [b*Skv, (b+1)*Skv) of
+// `k` / `v` (kv head h/group at column (h/group)*hd).  hd in {64, 72, 112}.  Used with Sq = chunk_len,
+// Skv = chunk_len + 65 + NP, hd = 112 for the Bridge-Attention core of the policy head.
+int cross_attention_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                           int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal,
+                           __nv_bfloat16* out, int ld_out, cudaStream_t s, const char** err);
+
 // Patch-embed im2col: pixel_values (B, 6*n_img, 224, 224) bf16 -> A[(b*n_img+i)*256 + p, 592]
 // with k = c*196 + ky*14 + kx (Conv2d weight order), columns 588..591 zero.  tower 0 reads channels
 // [6i, 6i+3) (DINOv2), tower 1 reads [6i+3, 6i+6) (SigLIP)  (modeling_prismatic.py:220-230).
@@ -61,21 +68,11 @@ int skinny_linear_launch(const void* x, int x_is_f32, int ldx, int M, int K, con
                          int N, const float* bias, int act, __nv_bfloat16* out, int ldo, float* out_f32,
                          cudaStream_t s, const char** err);
 
-// Bridge-Attention core (policy.cu); see policy.cu for the layout.
-struct PolicyAttnArgs {
-  const __nv_bfloat16* qkv_self;  // [B*T, 3*896]: q | k_self | v_self of the current x
-  const __nv_bfloat16* kv_a;      // [B, 64, 1792]  K|V of the ActionQuery rows (h_a)
-  const __nv_bfloat16* kv_p;      // [B, 1792] (+ row stride ld_p) K|V of the proprio row
-  int ld_p;
-  const __nv_bfloat16* kv_t;      // [B, NP, 1792] K|V of the task rows (h_t)
-  int B, T, NP;
-  float gate;                     // tanh(gating_factor)
-  int pro;                        // 0: base (gate on h_t segment, no RoPE); 1: Pro (RoPE, gate on h_t)
-  const float* rope_cos;          // [max_pos, 112] (Pro only; bf16-rounded fp32)
-  const float* rope_sin;
-  __nv_bfloat16* out;             // [B*T, 896]
-};
-int policy_attention_launch(const PolicyAttnArgs& a, cudaStream_t s, const char** err);
+// Pro-variant RoPE (action_heads.py:125-164, 381-386), in place: q rows (B*T, ld 896) at positions t, and the K
+// half of the per-sample key/value buffer kv [B][T+65+NP][1792]: self rows at positions 0..T-1, the 65
+// h_a ++ p rows at 0..64, the NP h_t rows at 0..NP-1.
+int policy_rope_launch(__nv_bfloat16* q, __nv_bfloat16* kv, int B, int T, int NP, const float* cos_t,
+                       const float* sin_t, cudaStream_t s, const char** err);
 
 // Final regression epilogue: out_norm[b,t,a] = fc2(LN(x)) ; out_unnorm = where(mask, 0.5*(a+1)*(hi-lo+1e-8)+lo, a)
 int head_out_launch(const __nv_bfloat16* x, int rows, const float* ln_w, const float* ln_b,
