@@ -323,12 +323,20 @@ def gather_hidden(states, num_patches, prompt_len):
 # Bridge-Attention policy head
 # =====================================================================================================
 def _head_rope_tables(n, dtype):
-    """RotaryPositionEmbedding.forward (AH:160-164), hd = 112."""
+    """RotaryPositionEmbedding.forward (AH:160-164), hd = 112, AS DEPLOYED: get_action_head casts the whole head
+    with `.to(torch.bfloat16)` (experiments/robot/openvla_utils.py:515; training does the same at
+    vla-scripts/finetune.py:281), which also casts the non-persistent `inv_freq` buffer (AH:158).  `t` is then
+    created in inv_freq's dtype (AH:161), so positions, the outer product and therefore the ANGLES are bf16
+    (positions above 256 are not even all representable).  Pinned bit-exactly by tests/golden/libero_pro.npz.
+    The fp32 "truth" keeps these deployed angles and evaluates cos/sin on them in fp32."""
     hd = D_LLM // HEAD_HEADS
-    inv = 1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))
-    fr = torch.einsum("i,j->ij", torch.arange(n, dtype=torch.float32), inv)
+    inv = (1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))).to(torch.bfloat16)
+    t = torch.arange(n, dtype=torch.bfloat16)
+    fr = torch.einsum("i,j->ij", t, inv)
     emb = torch.cat([fr, fr], dim=-1)
-    return emb.cos().to(dtype), emb.sin().to(dtype)
+    if dtype == torch.bfloat16:
+        return emb.cos(), emb.sin()
+    return emb.float().cos().to(dtype), emb.float().sin().to(dtype)
 
 
 def _apply_rope_one(x, cos, sin):

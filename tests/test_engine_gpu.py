@@ -85,3 +85,45 @@ def test_engine_error_paths():
     with pytest.raises(ValueError):          # missing tensors
         eng.finalize()
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["libero_base", "libero_pro", "single_image"])
+def test_engine_matches_reference_golden(name):
+    """The CUDA engine against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
+    oracle/make_golden.py): un-normalised actions within bf16 path noise of the reference's own bf16 run,
+    fp32 stage pins within 1e-2 relative L2 (bf16 storage of the taps), integer handling bit-exact."""
+    import os
+
+    from oracle.make_golden import STATS, case_config
+    from vla_adapter_b200 import tokens
+    from vla_adapter_b200.engine import VLAEngine
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    cfg, B, L, seed = case_config(name)
+    W = O.make_weights(cfg, seed=seed)
+    pix, ids, prop = O.make_inputs(cfg, B, L, seed=seed)
+    ext, labels, mask, aq, _ = tokens.build(ids, None, cfg.action_dim)
+    assert np.array_equal(ext.numpy(), g["ref_ext_ids"]) and np.array_equal(mask.numpy(), g["ref_mask"])
+    eng = VLAEngine(n_images=cfg.n_images, pro=cfg.pro, dino_depth=3, siglip_depth=3, vocab_size=2048, max_batch=B,
+                    max_prompt_len=L, norm_stats=STATS)
+    eng.load_flat(W)
+    eng.finalize()
+    actions, normalized, ha = eng.predict_action_batch(ids, None, pix, prop, unnorm_key="synthetic", return_hidden=True)
+    s = int(g["stride"])
+    for key, tap in [("ref32_projected", "projected"), ("ref32_llm_in", "llm_in"), ("ref32_hidden_1", "hidden.1"),
+                     ("ref32_hidden_12", "hidden.12"), ("ref32_hidden_24", "hidden.24")]:
+        got = eng.tap(tap).float().cpu().reshape(-1)[::s]
+        ref = torch.from_numpy(g[key])
+        assert _rel(got, ref) <= 1.5e-2, (name, key, _rel(got, ref))
+    # the bs=1 drop-in entry point returns the same numbers as the batched call
+    a0, h0 = eng.predict_action(ids[:1], "synthetic", prop[0].numpy(), pixel_values=pix[:1],
+                                attention_mask=torch.ones_like(ids[:1]))
+    eng.close()
+    assert actions.dtype == np.float64 and actions.shape == g["ref_actions"].shape
+    err = np.abs(actions - g["ref_actions"]).max()
+    print(f"{name}: max |engine - reference| on un-normalised actions = {err:.4f}")
+    assert err <= 4e-2
+    ref_ha = torch.from_numpy(g["ref_last_ha"]).view(torch.bfloat16).float()
+    assert _rel(ha.float().reshape(-1), ref_ha.reshape(-1)) <= 3e-2
+    assert a0.shape == (8, 7) and np.array_equal(a0, actions[0])
+    assert h0.shape == (1, 1, 64, 896) and h0.dtype == torch.bfloat16 and h0.is_cuda

@@ -65,9 +65,13 @@ __global__ void policy_rope_table_kernel(float* cos_t, float* sin_t, int max_pos
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= max_pos * PHD) return;
   const int pos = i / PHD, j = i % PHD;
-  // RotaryPositionEmbedding (action_heads.py:157-164): inv_freq = 1/10000^(2i/112), emb = cat(freqs, freqs)
-  const float inv_freq = static_cast<float>(1.0 / pow(10000.0, (2.0 * (j % (PHD / 2))) / PHD));
-  const float ang = static_cast<float>(pos) * inv_freq;
+  // RotaryPositionEmbedding (action_heads.py:157-164): inv_freq = 1/10000^(2i/112), emb = cat(freqs, freqs).
+  // AS DEPLOYED the head is cast with .to(torch.bfloat16) (experiments/robot/openvla_utils.py:515), which also
+  // casts the non-persistent inv_freq buffer; t = arange(dtype=inv_freq.dtype) (action_heads.py:161) and the
+  // outer product are then bf16 too, so the angle is bf16(bf16(t) * bf16(inv_freq)).  Pinned by
+  // tests/golden/libero_pro.npz.
+  const float inv_freq = bf16_round(1.0f / powf(10000.0f, static_cast<float>(2 * (j % (PHD / 2))) / PHD));
+  const float ang = bf16_round(bf16_round(static_cast<float>(pos)) * inv_freq);
   cos_t[i] = bf16_round(static_cast<float>(cos(static_cast<double>(ang))));
   sin_t[i] = bf16_round(static_cast<float>(sin(static_cast<double>(ang))));
 }
