@@ -33,7 +33,7 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
 def test_gemm_plain(M, N, K, bn):
     from vla_adapter_b200 import ops
 

@@ -29,51 +29,78 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB per stage
+constexpr uint32_t RING_BYTES = 192 * 1024;
+constexpr uint32_t STAGING_BYTES = EPI_WARPS * 2 * 2048;  // per epilogue warp: 2 x (32 rows x 64 B)
+constexpr uint32_t SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 512;        // two accumulators of up to 256 columns
+constexpr int MAX_STAGES = 8;
 
 struct GemmDev {
   int rows, batches, N, K;
   int mt_per_batch, tiles_m, tiles_n;
-  __nv_bfloat16* C;
-  long long c_bs;
-  int ldc;
+  int bn;          // tile width: 64 / 128 / 192 / 256
+  int stages;      // smem ring depth = min(8, 192 KB / stage bytes)
   const float* bias;
   const float* colscale;
-  const __nv_bfloat16* resid;
-  long long r_bs;
-  int ldr;
   int act;
+  int accumulate;  // 1: C += epi(...) through TMA reduce-add (C holds the residual)
 };
 
-template <int BN>
-struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr uint32_t A_BYTES = BM * BK * 2;
-  static constexpr uint32_t B_BYTES = BN * BK * 2;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 / 256 / 128: powers of two
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
+VLA_DEVINL void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 
-template <int BN>
+// One 32-row x 32-column output box of a warp: 16 packed bf16x2 words per thread (thread = row) go to the
+// warp's staging buffer in the 64-byte-swizzled layout the C tensor map expects, then one lane issues the
+// TMA store (or reduce-add).  OOB rows / columns are clipped by the TMA unit.
+VLA_DEVINL void store_box(const CUtensorMap* mapC, uint32_t buf_addr, int lane, const uint32_t (&o)[16], int c0,
+                          int r0, int b, int accumulate) {
+  if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer two boxes ago has read it
+  __syncwarp();
+  const uint32_t row_addr = buf_addr + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint32_t addr = row_addr + ((u ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[4 * u]), "r"(o[4 * u + 1]),
+                 "r"(o[4 * u + 2]), "r"(o[4 * u + 3])
+                 : "memory");
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    if (accumulate) tma_reduce_add_3d(mapC, buf_addr, c0, r0, b);
+    else tma_store_3d(mapC, buf_addr, c0, r0, b);
+    tma_store_commit();
+  }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA,
-                         const __grid_constant__ CUtensorMap mapB, const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                         const __grid_constant__ CUtensorMap mapC, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* smem = smem_raw + pad;
   const uint32_t smem_base = raw_addr + pad;
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const int STAGES = p.stages;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * BK * 2;
+  const uint32_t stage_bytes = A_BYTES + b_bytes;
+  const uint32_t staging_base = smem_base + RING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + STAGING_BYTES);
+  const uint32_t bar_base = smem_base + RING_BYTES + STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,19 +108,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA,
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), EPI_WARPS);
     }
     mbar_fence_init();
     fence_proxy_async();
   }
   if (warp_idx == 1) {
-    tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
     tc_fence_before();
   }
@@ -114,13 +142,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA,
         const int m_idx = tile / p.tiles_n;
         const int b = m_idx / p.mt_per_batch;
         const int r0 = (m_idx - b * p.mt_per_batch) * BM;
-        const int n0 = n_idx * BN;
+        const int n0 = n_idx * p.bn;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+          const uint32_t sa = smem_base + stage * stage_bytes;
           tma_load_3d(sa, &mapA, full_bar(stage), kb * BK, r0, b);
-          tma_load_3d(sa + Cfg::A_BYTES, &mapB, full_bar(stage), kb * BK, n0, 0);
+          tma_load_3d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0, 0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -131,7 +159,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA,
   } else if (warp_idx == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      const uint32_t idesc = make_idesc_bf16(BM, static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -139,12 +167,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA,
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_sw128_kmajor_desc(sa + k * 32);
@@ -163,110 +191,128 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA,
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (4 warps, 128 rows)
+    // ------------------------------------------------------------ epilogue: 8 warps, each 32 rows x bn/2 columns
+    const int e = warp_idx - 2;
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const int half = e >> 2;           // which half of the tile's columns
+    const int wcols = p.bn >> 1;       // accumulator columns per warp (multiple of 32)
+    const uint32_t buf0 = staging_base + static_cast<uint32_t>(e) * 4096u;
+    int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool swiglu = p.act == ACT_SWIGLU;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_idx = tile % p.tiles_n;
       const int m_idx = tile / p.tiles_n;
       const int b = m_idx / p.mt_per_batch;
-      const int r0 = (m_idx - b * p.mt_per_batch) * BM;
-      const int n0 = n_idx * BN;
-      const int r = r0 + quarter * 32 + lane;
-      const bool row_ok = r < p.rows;
+      const int r0 = (m_idx - b * p.mt_per_batch) * BM + quarter * 32;
+      const int n0 = n_idx * p.bn + half * wcols;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(acc * BN);
-      if (p.act == ACT_SWIGLU) {
-        __nv_bfloat16* crow = p.C + static_cast<long long>(b) * p.c_bs + static_cast<long long>(r) * p.ldc;
+                             static_cast<uint32_t>(acc * 256 + half * wcols);
+      if (r0 < p.rows && n0 < p.N) {  // warp-uniform: sub-tiles entirely out of bounds are skipped
+        if (swiglu) {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          const int c0 = n0 + ch * 32;
-          if (c0 >= p.N) break;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + ch * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            uint32_t o[8];
+          for (int ch = 0; ch < wcols; ch += 64) {
+            const int c0 = n0 + ch;
+            if (c0 >= p.N) break;
+            uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
-              const float u0 = __uint_as_float(v[16 + 2 * j]), u1 = __uint_as_float(v[16 + 2 * j + 1]);
-              o[j] = pack_bf16(silu(g0) * u0, silu(g1) * u1);
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(t_row + ch + hh * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
+                const float u0 = __uint_as_float(v[16 + 2 * j]), u1 = __uint_as_float(v[16 + 2 * j + 1]);
+                o[hh * 8 + j] = pack_bf16(silu(g0) * u0, silu(g1) * u1);
+              }
             }
-            uint4* dst = reinterpret_cast<uint4*>(crow + (c0 >> 1));
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            store_box(&mapC, buf0 + buf * 2048u, lane, o, c0 >> 1, r0, b, 0);
+            buf ^= 1;
           }
-        }
-      } else {
-        __nv_bfloat16* crow = p.C + static_cast<long long>(b) * p.c_bs + static_cast<long long>(r) * p.ldc;
-        const __nv_bfloat16* rrow =
-            p.resid ? p.resid + static_cast<long long>(b) * p.r_bs + static_cast<long long>(r) * p.ldr
-                    : nullptr;
+        } else {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          const int c0 = n0 + ch * 32;
-          if (c0 >= p.N) break;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + ch * 32, v);
-          tmem_ld_wait();
+          for (int ch = 0; ch < wcols; ch += 32) {
+            const int c0 = n0 + ch;
+            if (c0 >= p.N) break;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + ch, v);
+            float2 f[16];
+            if (p.bias) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = c0 + q * 8;
-            if (c < p.N && row_ok) {
-              float f[8];
+              for (int q = 0; q < 8; ++q) {
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + q * 4 < p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + q * 4));
+                f[2 * q] = make_float2(bv.x, bv.y);
+                f[2 * q + 1] = make_float2(bv.z, bv.w);
+              }
+            } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (p.act == ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
-              } else if (p.act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
-              }
-              if (p.colscale) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.colscale + c));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.colscale + c + 4));
-                f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-                f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-              }
-              if (rrow) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c);
-                const float2 r0v = unpack_bf16(rv.x), r1v = unpack_bf16(rv.y);
-                const float2 r2v = unpack_bf16(rv.z), r3v = unpack_bf16(rv.w);
-                f[0] += r0v.x; f[1] += r0v.y; f[2] += r1v.x; f[3] += r1v.y;
-                f[4] += r2v.x; f[5] += r2v.y; f[6] += r3v.x; f[7] += r3v.y;
-              }
-              *reinterpret_cast<uint4*>(crow + c) =
-                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                             pack_bf16(f[6], f[7]));
+              for (int j = 0; j < 16; ++j) f[j] = make_float2(0.f, 0.f);
             }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              f[j] = __fadd2_rn(f[j], make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+            if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
+            } else if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = make_float2(fmaxf(f[j].x, 0.0f), fmaxf(f[j].y, 0.0f));
+            }
+            if (p.colscale) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + q * 4 < p.N) sv = __ldg(reinterpret_cast<const float4*>(p.colscale + c0 + q * 4));
+                f[2 * q] = __fmul2_rn(f[2 * q], make_float2(sv.x, sv.y));
+                f[2 * q + 1] = __fmul2_rn(f[2 * q + 1], make_float2(sv.z, sv.w));
+              }
+            }
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = pack_bf16(f[j].x, f[j].y);
+            store_box(&mapC, buf0 + buf * 2048u, lane, o, c0, r0, b, p.accumulate);
+            buf ^= 1;
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) tma_store_wait_read<0>();  // staging smem must outlive the last bulk reads
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// dst view = src view (bf16 rows of `cols` elements, 16-byte vectors); src batch stride may be 0 (broadcast)
+__global__ void __launch_bounds__(256)
+copy_view_kernel(const __nv_bfloat16* __restrict__ src, long long s_bs, int lds, __nv_bfloat16* __restrict__ dst,
+                 long long d_bs, int ldd, int rows, int batches, int cols) {
+  const int nvec = cols >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(batches) * rows * nvec;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % nvec);
+  const long long t = idx / nvec;
+  const int r = static_cast<int>(t % rows);
+  const long long b = t / rows;
+  *reinterpret_cast<uint4*>(dst + b * d_bs + static_cast<long long>(r) * ldd + v * 8) =
+      *reinterpret_cast<const uint4*>(src + b * s_bs + static_cast<long long>(r) * lds + v * 8);
 }
 
 // ------------------------------------------------------------------ host side
@@ -289,18 +335,21 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 3-D bf16 map: dims (inner, rows, batches), box (64, box_rows, 1), 128B swizzle, zero OOB fill.
+// 3-D bf16 map: dims (inner, rows, batches), box (box_inner, box_rows, 1), zero OOB fill.
+// Operand maps use 64-element (128 B) boxes with 128B swizzle; the output map uses 32-element (64 B) boxes
+// with 64B swizzle (the epilogue's staging layout).
 bool make_map_3d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t batches,
-                 uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows) {
+                 uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_inner, uint32_t box_rows,
+                 CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {inner, rows, batches};
   cuuint64_t strides[2] = {row_stride_elems * 2, batch_stride_elems * 2};
-  cuuint32_t box[3] = {BK, box_rows, 1};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -326,44 +375,6 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
-}
-
-template <int BN>
-int launch_bn(const CUtensorMap& mA, const CUtensorMap& mB, const GemmDev& p, cudaStream_t stream,
-              const char** err) {
-  using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg::SMEM_BYTES) != cudaSuccess) {
-      if (err) *err = "gemm: cudaFuncSetAttribute(max dynamic smem) failed";
-      return -4;
-    }
-    attr_set = true;
-  }
-  const int total = p.tiles_m * p.tiles_n;
-  const int grid = total < num_sms() ? total : num_sms();
-  ProfRec rec{};
-  rec.rows = p.rows; rec.batches = p.batches; rec.N = p.N; rec.K = p.K; rec.bn = BN; rec.act = p.act;
-  const bool prof = g_prof_on;
-  if (prof) {
-    cudaEventCreate(&rec.e0);
-    cudaEventCreate(&rec.e1);
-    cudaEventRecord(rec.e0, stream);
-  }
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mA, mB, p);
-  if (prof) {
-    cudaEventRecord(rec.e1, stream);
-    std::lock_guard<std::mutex> lk(g_prof_mu);
-    g_prof.push_back(rec);
-  }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    if (err) *err = cudaGetErrorString(e);
-    return -4;
-  }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return 0;
 }
 
 }  // namespace
@@ -418,29 +429,50 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     if (err) *err = "gemm: residual view must be 16-byte aligned";
     return -1;
   }
-  if (a.act == ACT_SWIGLU && (a.N & 31)) {
-    if (err) *err = "gemm: SwiGLU epilogue needs N % 32 == 0";
+  const bool swiglu = a.act == ACT_SWIGLU;
+  if (swiglu && ((a.N & 63) || a.resid)) {
+    if (err) *err = "gemm: SwiGLU epilogue needs N % 64 == 0 and takes no residual";
     return -1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_BYTES) != cudaSuccess) {
+      if (err) *err = "gemm: cudaFuncSetAttribute(max dynamic smem) failed";
+      return -4;
+    }
+    attr_set = true;
   }
 
   const int mt_per_batch = (a.rows + BM - 1) / BM;
   const int tiles_m = mt_per_batch * a.batches;
-  // Tile-width heuristic: fewest "waves x tile width" over the SM count.
+  const int sms = num_sms();
+  // Tile-width heuristic: fewest (rounds over the SMs) x (tile width + fixed per-tile cost).
   int bn = a.force_bn;
-  if (bn != 64 && bn != 128 && bn != 256) {
-    const int sms = num_sms();
+  if (bn != 64 && bn != 128 && bn != 192 && bn != 256) {
     long long best = -1;
-    const int cands[3] = {256, 128, 64};
-    for (int i = 0; i < 3; ++i) {
+    const int cands[4] = {256, 192, 128, 64};
+    for (int i = 0; i < 4; ++i) {
       const int c = cands[i];
+      if (swiglu && (c & 127)) continue;  // a SwiGLU output box needs 64 accumulator columns per warp
       const long long tiles = static_cast<long long>(tiles_m) * ((a.N + c - 1) / c);
-      const long long waves = (tiles + sms - 1) / sms;
-      const long long cost = waves * (c + 24);
+      const long long rounds = (tiles + sms - 1) / sms;
+      const long long cost = rounds * (c + 96);  // measured: narrow tiles pay ~96 columns of fixed cost
       if (best < 0 || cost < best) {
         best = cost;
         bn = c;
       }
     }
+  }
+  if (swiglu && (bn & 127)) bn = 128;
+
+  // Residual: the epilogue adds into C with a TMA reduce-add, so C must hold the residual first.
+  const bool accumulate = a.resid != nullptr;
+  if (accumulate && !(a.resid == a.C && a.ldr == a.ldc && (a.batches == 1 || a.r_batch_stride == a.c_batch_stride))) {
+    const long long total = static_cast<long long>(a.batches) * a.rows * (a.N >> 3);
+    copy_view_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        a.resid, a.r_batch_stride, a.ldr, a.C, a.c_batch_stride, a.ldc, a.rows, a.batches, a.N);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
 
   GemmDev p;
@@ -451,27 +483,52 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.mt_per_batch = mt_per_batch;
   p.tiles_m = tiles_m;
   p.tiles_n = (a.N + bn - 1) / bn;
-  p.C = a.C;
-  p.c_bs = a.c_batch_stride;
-  p.ldc = a.ldc;
+  p.bn = bn;
+  const uint32_t stage_bytes = A_BYTES + static_cast<uint32_t>(bn) * BK * 2;
+  p.stages = static_cast<int>(RING_BYTES / stage_bytes);
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.bias = a.bias;
   p.colscale = a.colscale;
-  p.resid = a.resid;
-  p.r_bs = a.r_batch_stride;
-  p.ldr = a.ldr;
   p.act = a.act;
+  p.accumulate = accumulate ? 1 : 0;
 
-  CUtensorMap mA, mB;
+  CUtensorMap mA, mB, mC;
   const uint64_t a_bs = a.batches > 1 ? static_cast<uint64_t>(a.a_batch_stride)
                                       : static_cast<uint64_t>(a.rows) * a.lda;
-  if (!make_map_3d(&mA, a.A, a.K, a.rows, a.batches, a.lda, a_bs, BM) ||
-      !make_map_3d(&mB, a.W, a.K, a.N, 1, a.ldw, static_cast<uint64_t>(a.N) * a.ldw, bn)) {
+  const uint64_t c_bs = a.batches > 1 ? static_cast<uint64_t>(a.c_batch_stride)
+                                      : static_cast<uint64_t>(a.rows) * a.ldc;
+  const uint64_t n_out = swiglu ? a.N / 2 : a.N;
+  if (!make_map_3d(&mA, a.A, a.K, a.rows, a.batches, a.lda, a_bs, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !make_map_3d(&mB, a.W, a.K, a.N, 1, a.ldw, static_cast<uint64_t>(a.N) * a.ldw, BK, bn,
+                   CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !make_map_3d(&mC, a.C, n_out, a.rows, a.batches, a.ldc, c_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) {
     if (err) *err = "gemm: cuTensorMapEncodeTiled failed";
     return -4;
   }
-  if (bn == 256) return launch_bn<256>(mA, mB, p, stream, err);
-  if (bn == 128) return launch_bn<128>(mA, mB, p, stream, err);
-  return launch_bn<64>(mA, mB, p, stream, err);
+
+  const int total = p.tiles_m * p.tiles_n;
+  const int grid = total < sms ? total : sms;
+  ProfRec rec{};
+  rec.rows = p.rows; rec.batches = p.batches; rec.N = p.N; rec.K = p.K; rec.bn = bn; rec.act = p.act;
+  const bool prof = g_prof_on;
+  if (prof) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    cudaEventRecord(rec.e0, stream);
+  }
+  gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(mA, mB, mC, p);
+  if (prof) {
+    cudaEventRecord(rec.e1, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = cudaGetErrorString(e);
+    return -4;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 }  // namespace vla
