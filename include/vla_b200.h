@@ -148,6 +148,11 @@ int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_of
                      int n_heads, int group, int hd, int causal, void* out, int ld_out,
                      void* stream);
 
+/* Attention kernel selection for vla_op_attention and the engine: 0 = auto (tcgen05/TMEM/TMA kernel for head
+ * dims 64 and 72, the small mma.sync kernel for the policy's 8-query hd-112 cross-attention), 1 = mma.sync
+ * kernel everywhere (A/B comparison), 2 = tcgen05 kernel whenever the head dim allows.  Returns 0. */
+int vla_set_attention_impl(int impl);
+
 /* In-place HF rotate_half RoPE (theta) on `n_heads` heads of width 64 starting at column `off`
  * of each row; position = row % S. */
 int vla_op_rope(void* x, int ld, int off, int n_heads, int B, int S, float theta, void* stream);

@@ -148,16 +148,45 @@ def _ref_attention(qkv, B, S, H, HKV, hd, causal):
     (1, 609, 14, 2, 64, False),    # bidirectional LLM mode
     (3, 64, 14, 2, 64, True),
     (1, 1, 16, 16, 72, False),
+    (2, 128, 16, 16, 64, False),   # exactly one tile
+    (1, 129, 14, 2, 64, True),     # one row into the second tile
+    (2, 400, 16, 16, 72, True),
 ])
-def test_attention(B, S, H, HKV, hd, causal):
+@pytest.mark.parametrize("impl", [1, 2])   # 1 = mma.sync kernel, 2 = tcgen05/TMEM kernel
+def test_attention(B, S, H, HKV, hd, causal, impl):
     from vla_adapter_b200 import ops
 
     qkv = _randn(B * S, (H + 2 * HKV) * hd, seed=13)
-    out = ops.attention(qkv, B, S, H, HKV, hd, causal)
+    ops.set_attention_impl(impl)
+    try:
+        out = ops.attention(qkv, B, S, H, HKV, hd, causal)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_attention_impl(0)
     ref = _ref_attention(qkv, B, S, H, HKV, hd, causal)
     assert torch.isfinite(out.float()).all()
     assert (out.float() - ref).abs().max().item() < 2e-2
     assert _rel(out, ref) < 1e-2
+
+
+def test_attention_large_scores_rescale():
+    """Scores that grow by far more than 2^8 from one key tile to the next exercise the lazy O rescale of the
+    tcgen05 kernel; the softmax is then nearly one-hot and must still match the fp32 reference."""
+    from vla_adapter_b200 import ops
+
+    B, S, H, hd = 1, 640, 16, 64
+    qkv = _randn(B * S, 3 * H * hd, seed=21)
+    k = qkv[:, H * hd:2 * H * hd].view(S, H, hd)
+    k *= torch.linspace(0.2, 6.0, S, device="cuda").to(torch.bfloat16)[:, None, None]   # later keys score higher
+    ops.set_attention_impl(2)
+    try:
+        out = ops.attention(qkv, B, S, H, H, hd, False)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_attention_impl(0)
+    ref = _ref_attention(qkv, B, S, H, H, hd, False)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 1.5e-2
 
 
 def test_rope():

@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("VLA_NVCC_EXTRA", "").split()   # e.g. -DVLA_FA_TRACE_BUILD for the attention event trace
 
 
 def _nvcc() -> str:

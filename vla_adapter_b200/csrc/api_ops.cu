@@ -83,6 +83,11 @@ int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_of
   return rc ? fail(rc, err) : 0;
 }
 
+int vla_set_attention_impl(int impl) {
+  vla::attention_set_impl(impl);
+  return 0;
+}
+
 int vla_op_rope(void* x, int ld, int off, int n_heads, int B, int S, float theta, void* stream) {
   const char* err = nullptr;
   int rc = vla::rope_launch(static_cast<__nv_bfloat16*>(x), ld, off, n_heads, B, S, theta,

@@ -259,6 +259,9 @@ int launch_attn(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k
 
 }  // namespace
 
+static int g_attn_impl = 0;  // 0 = auto, 1 = force the mma.sync kernel, 2 = force tcgen05 whenever the head dim allows
+void attention_set_impl(int impl) { g_attn_impl = impl; }
+
 int attention_launch(const __nv_bfloat16* qkv, int ld_qkv, int q_off, int k_off, int v_off, int B, int S,
                      int n_heads, int group, int hd, int causal, __nv_bfloat16* out, int ld_out,
                      cudaStream_t s, const char** err) {
@@ -283,6 +286,11 @@ int cross_attention_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_
   if (causal && Sq != Skv) {
     if (err) *err = "attention: causal masking needs Sq == Skv";
     return -1;
+  }
+  // The large shapes (hd 64 / 72, at least one full-ish query tile) run on the tcgen05 kernel (attention_tc.cu).
+  if (g_attn_impl != 1 && (hd == 64 || hd == 72) && (Sq >= 32 || g_attn_impl == 2)) {
+    const int rc = attention_tc_launch(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, hd, causal, out, ld_out, s, err);
+    if (rc <= 0) return rc;
   }
   if (hd == 64) return launch_attn<64, 64>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, causal, out, ld_out, s, err);
   if (hd == 72) return launch_attn<72, 80>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, causal, out, ld_out, s, err);

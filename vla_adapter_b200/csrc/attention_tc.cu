@@ -1,0 +1,736 @@
+// softmax(Q K^T / sqrt(hd)) V on tcgen05 tensor cores with TMEM accumulators, operands fed by TMA.
+//
+// Serves the three big attention shapes of the path (head dims 64 and 72; the policy's 8-query
+// cross-attention stays on the small mma.sync kernel of attention.cu):
+//   DINOv2  : 16 heads x 64, S = 261, bidirectional   (timm Attention restated in film_vit_wrapper.py:69)
+//   SigLIP  : 16 heads x 72, S = 256, bidirectional
+//   Qwen2.5 : 14 q / 2 kv heads x 64, S ~ 625, causal (modeling_prismatic.py:834-845 -> Qwen2Attention)
+//
+// Persistent kernel, one CTA per SM.  A work item is a PAIR of 128-row query tiles ("slots" A and B) that share
+// one K/V stream: two query tiles of one head (ViT) or two query heads of one kv group (Qwen GQA), so every K/V
+// tile is fetched once for 256 query rows.  Roles (384 threads = 3 warpgroups; setmaxnreg moves registers from warpgroup 0 to the softmax warpgroups):
+//   warp 0    : TMA producer - Q tiles of both slots, K/V tiles of 128 keys through an mbarrier ring that runs
+//                              ahead across work items (the next item's operands land while this one computes)
+//   warp 1    : MMA issuer   - per slot S = Q K^T (SS, 128 x keys x hd) into TMEM, then O += P V (TS: P is read
+//                              from TMEM, V is the MN-major smem operand); tcgen05.commit -> mbarriers.  The two
+//                              slots are interleaved so the tensor pipe works on one while the other is in softmax.
+//   warps 4-7 : softmax + epilogue of slot A, warps 8-11 of slot B - one thread per query row: tcgen05.ld the
+//                              fp32 score row, mask, running max with lazy rescaling of O (only when the max grows
+//                              by > 2^8), exp2, row sum, P -> bf16 -> tcgen05.st over the score columns; finally
+//                              O / l -> bf16 -> global.
+// TMEM columns: [0,128) S_A (P_A aliases [0,64)), [128,256) S_B, [256,256+hd) O_A, [384,384+hd) O_B.
+//
+// Head dim 72 is handled as a 64-wide main block (128B-swizzled tiles) plus a 16-wide tail block
+// (32B-swizzled tiles) whose columns 72..79 are zero-filled by TMA: the tensor maps are per-head 4-D views
+// (d, head, row, sample) so that out-of-head columns count as out of bounds.
+#include "common.cuh"
+#include "ops.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+namespace vla {
+
+namespace {
+
+constexpr int FA_BM = 128;
+constexpr int FA_BN = 128;
+constexpr int FA_THREADS = 384;  // warpgroup 0: TMA + MMA warps (+2 idle), warpgroups 1/2: softmax of slot A/B
+constexpr uint32_t FA_TMEM_COLS = 512;
+constexpr uint32_t FA_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+constexpr uint32_t FA_TAIL_BYTES = 128 * 32;   // 128 rows x 16 bf16
+constexpr int FA_MAX_ITEMS = 24;               // work items per (sample, kv head)
+
+struct FaDev {
+  int Sq, Skv, group, kv_heads, causal;
+  int n_bg;     // samples * kv heads
+  int n_items;  // n_bg * items per (sample, kv head)
+  float scale_log2;
+  __nv_bfloat16* out;
+  int ld_out;
+  unsigned int* trace;  // timing experiments only (VLA_FA_TRACE): [0] = count, then (event, clock) pairs of CTA 0
+  int debug;  // timing experiments only (VLA_FA_DEBUG): 1 = no softmax math, 2 = no PV MMAs, 4 = no QK MMAs
+  // per (sample, kv head): query head (relative to the group) and query tile of slot A / slot B, packed
+  // hA | qA << 8 | hB << 16 | qB << 24; hB == 0xff: slot B idle
+  uint32_t items[FA_MAX_ITEMS];
+};
+
+struct FaItem {
+  int b, g;
+  int h[2], qb[2], n[2];  // per slot: absolute query head, query tile, number of key tiles (0 = idle)
+  int nmax;
+};
+
+// Debug event log of CTA 0 (VLA_FA_TRACE): four single-writer regions (producer, MMA, softmax A, softmax B) of 4000
+// (event, clock) pairs each, written fire-and-forget so that tracing barely perturbs the timeline.
+// Compiled in only with -DVLA_FA_TRACE_BUILD (the bookkeeping costs registers in the softmax warps).
+VLA_DEVINL void fa_trace(const FaDev& p, int role, unsigned int& cnt, unsigned int ev) {
+#ifdef VLA_FA_TRACE_BUILD
+  if (p.trace && blockIdx.x == 0 && cnt < 4000) {
+    unsigned int* dst = p.trace + 4 + role * 8000 + 2 * cnt;
+    dst[0] = ev;
+    dst[1] = static_cast<unsigned int>(clock64());
+    ++cnt;
+    p.trace[role] = cnt;
+  }
+#endif
+}
+
+VLA_DEVINL FaItem fa_decode(const FaDev& p, int item) {
+  FaItem it;
+  const int r = item / p.n_bg, bg = item - r * p.n_bg;
+  it.b = bg / p.kv_heads;
+  it.g = bg - it.b * p.kv_heads;
+  const uint32_t w = p.items[r];
+  const int n_all = (p.Skv + FA_BN - 1) / FA_BN;
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    const int hr = (w >> (16 * x)) & 0xff, q = (w >> (16 * x + 8)) & 0xff;
+    it.h[x] = it.g * p.group + hr;
+    it.qb[x] = q;
+    it.n[x] = hr == 0xff ? 0 : ((p.causal && q + 1 < n_all) ? q + 1 : n_all);
+  }
+  it.nmax = it.n[0] > it.n[1] ? it.n[0] : it.n[1];
+  return it;
+}
+
+VLA_DEVINL void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// Generic shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1).
+VLA_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;  // LBO: unused by every layout in this kernel (single atom along MN / K)
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
+}
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW32 = 6;
+
+// D[tmem] (+)= A[tmem] * B[smem]
+VLA_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+VLA_DEVINL void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+VLA_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+      "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+VLA_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+VLA_DEVINL float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Softmax of one 128-row x (NLIVE*32)-key score tile for this thread's query row: scores from TMEM, mask, running
+// max with lazy O rescale, exp2, row sum, P (bf16) back over the score columns.
+template <int HD, int NLIVE>
+VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tS, uint32_t tO, int k0, int wrow0, int grow, int j, float sl2,
+                                float& m_ref, float& l, int tr_role, unsigned int& tr_cnt) {
+#ifdef VLA_FA_TRACE_BUILD
+  const bool tr = tr_role >= 0;
+#else
+  constexpr bool tr = false;
+#endif
+  uint32_t v[NLIVE][32];
+#pragma unroll
+  for (int c = 0; c < NLIVE; ++c) tmem_ld_32x32b_x32(tS + c * 32, v[c]);
+  tmem_ld_wait();
+  if (tr) fa_trace(p, tr_role, tr_cnt, 700);
+#pragma unroll
+  for (int c = 0; c < NLIVE; ++c) {
+    const int c0 = k0 + c * 32;
+    if (c0 + 32 > p.Skv || (p.causal && c0 + 31 > wrow0)) {  // warp-uniform: chunk touches the diagonal or the tail
+      int last = p.Skv - 1;                      // last key this row may attend to ...
+      if (p.causal && grow < last) last = grow;
+      last -= c0;                                // ... relative to this chunk
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i > last) v[c][i] = 0xff800000u;     // -inf
+    }
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NLIVE; ++c) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      mx0 = fmaxf(mx0, __uint_as_float(v[c][i]));
+      mx1 = fmaxf(mx1, __uint_as_float(v[c][i + 1]));
+      mx2 = fmaxf(mx2, __uint_as_float(v[c][i + 2]));
+      mx3 = fmaxf(mx3, __uint_as_float(v[c][i + 3]));
+    }
+  }
+  const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+  if (j == 0) {
+    m_ref = m_new;
+  } else {
+    // Lazy rescale: the reference max only moves when it would otherwise let exp2 exceed 2^8.
+    const bool need = (m_new - m_ref) * sl2 > 8.0f;
+    if (__any_sync(0xffffffffu, need)) {
+      const float alpha = need ? ex2f((m_ref - m_new) * sl2) : 1.0f;
+      if (need) m_ref = m_new;
+      l *= alpha;
+      // s_full(j) was committed after PV(j-1), so O is stable here and PV(j) has not been issued yet.
+#pragma unroll 1
+      for (int c = 0; c < (HD + 31) / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tO + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32b_x32(tO + c * 32, o);
+      }
+    }
+  }
+  const float mb = m_ref * sl2;
+  float s0 = 0.f, s1 = 0.f;
+  if (tr) fa_trace(p, tr_role, tr_cnt, 701);
+  const float2 sl2v = make_float2(sl2, sl2), nmb = make_float2(-mb, -mb);
+  float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < NLIVE; ++c) {
+    // phase 1: all 32 exponentials of the chunk in flight (packed FFMA2 for the scale/shift)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2v, nmb);
+      v[c][2 * i] = __float_as_uint(ex2f(t.x));
+      v[c][2 * i + 1] = __float_as_uint(ex2f(t.y));
+    }
+    // phase 2: row sum (packed FADD2) and bf16 packing
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 e = make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]));
+      sum2 = __fadd2_rn(sum2, e);
+      pk[i] = pack_bf16(e.x, e.y);
+    }
+    tmem_st_32x32b_x16(tS + c * 16, pk);
+  }
+  s0 = sum2.x;
+  s1 = sum2.y;
+  if (tr) fa_trace(p, tr_role, tr_cnt, 703);
+  l += s0 + s1;
+}
+
+template <int HD>
+struct FaSmem {
+  static constexpr bool TAIL = HD > 64;
+  static constexpr int STAGES = TAIL ? 3 : 4;
+  static constexpr int QBUFS = 4;  // 2 slots x 2 buffers: the next item's Q tiles land while this item computes
+  static constexpr uint32_t Q_BYTES = FA_TILE_BYTES + (TAIL ? FA_TAIL_BYTES : 0);
+  static constexpr uint32_t KV_BYTES = 2 * FA_TILE_BYTES + (TAIL ? 2 * FA_TAIL_BYTES : 0);
+  // main tiles first (1024-byte aligned), then the 32B-swizzled tails, then barriers
+  static constexpr uint32_t OFF_Q = 0;                               // QBUFS
+  static constexpr uint32_t OFF_K = QBUFS * FA_TILE_BYTES;           // STAGES
+  static constexpr uint32_t OFF_V = OFF_K + STAGES * FA_TILE_BYTES;  // STAGES
+  static constexpr uint32_t OFF_QT = OFF_V + STAGES * FA_TILE_BYTES;
+  static constexpr uint32_t OFF_KT = OFF_QT + QBUFS * FA_TAIL_BYTES;
+  static constexpr uint32_t OFF_VT = OFF_KT + STAGES * FA_TAIL_BYTES;
+  static constexpr uint32_t OFF_BAR = TAIL ? OFF_VT + STAGES * FA_TAIL_BYTES : OFF_QT;
+  static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024 /*align slack*/;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(FA_THREADS, 1)
+fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                  const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapQt,
+                  const __grid_constant__ CUtensorMap mapKt, const __grid_constant__ CUtensorMap mapVt,
+                  const __grid_constant__ FaDev p) {
+  using L = FaSmem<HD>;
+  constexpr bool TAIL = L::TAIL;
+  constexpr int NS = L::STAGES;
+
+  extern __shared__ uint8_t fa_smem_raw[];
+  const uint32_t raw_addr = smem_u32(fa_smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = fa_smem_raw + pad;
+  const uint32_t sbase = raw_addr + pad;
+  const uint32_t bar_base = sbase + L::OFF_BAR;
+  auto q_full = [&](int qb) { return bar_base + 8u * qb; };          // qb = slot * 2 + buffer
+  auto q_empty = [&](int qb) { return bar_base + 8u * (4 + qb); };
+  auto s_full = [&](int x) { return bar_base + 8u * (8 + x); };
+  auto p_ready = [&](int x) { return bar_base + 8u * (10 + x); };
+  auto o_full = [&](int x) { return bar_base + 8u * (12 + x); };
+  auto o_empty = [&](int x) { return bar_base + 8u * (14 + x); };
+  auto kv_full = [&](int s) { return bar_base + 8u * (18 + s); };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (18 + NS + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_BAR + 8 * (18 + 2 * NS));
+
+  // shfl-broadcast warp index: the role branches are then provably warp-uniform, so the MMA warp's descriptor
+  // arithmetic stays on the uniform datapath and tcgen05.mma issues at the hardware rate (scripts/ubench/mma3.cu)
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    for (int qb = 0; qb < 4; ++qb) {
+      mbar_init(q_full(qb), 1);
+      mbar_init(q_empty(qb), 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(s_full(x), 1);
+      mbar_init(p_ready(x), 128);
+      mbar_init(o_full(x), 1);
+      mbar_init(o_empty(x), 128);
+    }
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    mbar_fence_init();
+    fence_proxy_async();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc(smem_u32(tmem_slot), FA_TMEM_COLS);
+    tmem_relinquish();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp_idx < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp_idx == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp waits, one lane issues)
+    uint32_t kv_cnt = 0, q_cnt[2] = {0, 0};
+    unsigned int tr_cnt = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const FaItem it = fa_decode(p, item);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (!it.n[x]) continue;
+        const int qb = x * 2 + static_cast<int>(q_cnt[x] & 1u);
+        mbar_wait(q_empty(qb), ((q_cnt[x] >> 1) & 1u) ^ 1u);
+        ++q_cnt[x];
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full(qb), L::Q_BYTES);
+          tma_load_4d(sbase + L::OFF_Q + qb * FA_TILE_BYTES, &mapQ, q_full(qb), 0, it.h[x], it.qb[x] * FA_BM, it.b);
+          if (TAIL)
+            tma_load_4d(sbase + L::OFF_QT + qb * FA_TAIL_BYTES, &mapQt, q_full(qb), 64, it.h[x], it.qb[x] * FA_BM, it.b);
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < it.nmax; ++j) {
+        const int s = static_cast<int>(kv_cnt % NS);
+        const uint32_t ph = (kv_cnt / NS) & 1u;
+        ++kv_cnt;
+        mbar_wait(kv_empty(s), ph ^ 1u);
+        if (elect_one()) {
+          fa_trace(p, 0, tr_cnt, 100 + j);
+          mbar_arrive_expect_tx(kv_full(s), L::KV_BYTES);
+          tma_load_4d(sbase + L::OFF_K + s * FA_TILE_BYTES, &mapK, kv_full(s), 0, it.g, j * FA_BN, it.b);
+          tma_load_4d(sbase + L::OFF_V + s * FA_TILE_BYTES, &mapV, kv_full(s), 0, it.g, j * FA_BN, it.b);
+          if (TAIL) {
+            tma_load_4d(sbase + L::OFF_KT + s * FA_TAIL_BYTES, &mapKt, kv_full(s), 64, it.g, j * FA_BN, it.b);
+            tma_load_4d(sbase + L::OFF_VT + s * FA_TAIL_BYTES, &mapVt, kv_full(s), 64, it.g, j * FA_BN, it.b);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ------------------------------------------------------------ MMA issuer (whole warp waits, one lane issues)
+    uint32_t kv_cnt = 0, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0}, o_cnt[2] = {0, 0};
+    unsigned int tr_cnt = 0;
+    const uint32_t idesc_pv = make_idesc_bf16(128, 64) | (1u << 16);
+    const uint32_t idesc_pvt = make_idesc_bf16(128, 16) | (1u << 16);
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const FaItem it = fa_decode(p, item);
+      const uint32_t kv0 = kv_cnt;  // ring position of this item's key tile 0
+      kv_cnt += static_cast<uint32_t>(it.nmax);
+      int kv_waited = 0;            // key tiles [0, kv_waited) of this item are known to have landed
+      auto stage_of = [&](int j) { return static_cast<int>((kv0 + j) % NS); };
+      auto need_kv = [&](int j) {
+        while (kv_waited <= j) {
+          const uint32_t c = kv0 + kv_waited;
+          mbar_wait(kv_full(static_cast<int>(c % NS)), (c / NS) & 1u);
+          ++kv_waited;
+        }
+        tc_fence_after();
+      };
+      auto n16_of = [&](int j) {
+        int nvalid = p.Skv - j * FA_BN;
+        if (nvalid > FA_BN) nvalid = FA_BN;
+        return (nvalid + 15) >> 4;  // key columns actually computed, in units of 16
+      };
+      int qbuf[2] = {0, 0};
+      // S_x = Q_x K_j^T   (M = 128 query rows, N = n16*16 keys, K = head dim)
+      auto issue_qk = [&](int x, int j) {
+        need_kv(j);
+        const int s = stage_of(j);
+        const uint32_t tS = tmem_base + 128u * x;
+        const uint32_t idesc_qk = make_idesc_bf16(128, static_cast<uint32_t>(n16_of(j) * 16));
+        const uint32_t sq = sbase + L::OFF_Q + qbuf[x] * FA_TILE_BYTES, sk = sbase + L::OFF_K + s * FA_TILE_BYTES;
+        if (elect_one()) {
+          if (!(p.debug & 4)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tS, make_smem_desc(sq + k * 32, 1024, LAYOUT_SW128),
+                        make_smem_desc(sk + k * 32, 1024, LAYOUT_SW128), idesc_qk, k != 0 ? 1u : 0u);
+            if (TAIL)
+              umma_bf16(tS, make_smem_desc(sbase + L::OFF_QT + qbuf[x] * FA_TAIL_BYTES, 256, LAYOUT_SW32),
+                        make_smem_desc(sbase + L::OFF_KT + s * FA_TAIL_BYTES, 256, LAYOUT_SW32), idesc_qk, 1u);
+          }
+          umma_commit(s_full(x));
+          if (j == it.n[x] - 1) umma_commit(q_empty(qbuf[x]));  // last use of this Q tile
+        }
+        __syncwarp();
+      };
+      // O_x (+)= P_x V_j   (A = P from TMEM, B = V MN-major: K = keys, N = head dim)
+      auto issue_pv = [&](int x, int j) {
+        const int s = stage_of(j);
+        const int n16 = n16_of(j);
+        const uint32_t tS = tmem_base + 128u * x, tO = tmem_base + 256u + 128u * x;
+        const uint32_t sv = sbase + L::OFF_V + s * FA_TILE_BYTES;
+        if (elect_one()) {
+          if (!(p.debug & 2)) {
+            for (int kk = 0; kk < n16; ++kk)
+              umma_bf16_ts(tO, tS + kk * 8, make_smem_desc(sv + kk * 2048, 1024, LAYOUT_SW128), idesc_pv,
+                           (j | kk) != 0 ? 1u : 0u);
+            if (TAIL) {
+              const uint32_t svt = sbase + L::OFF_VT + s * FA_TAIL_BYTES;
+              for (int kk = 0; kk < n16; ++kk)
+                umma_bf16_ts(tO + 64, tS + kk * 8, make_smem_desc(svt + kk * 512, 256, LAYOUT_SW32), idesc_pvt,
+                             (j | kk) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        __syncwarp();
+      };
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (!it.n[x]) continue;
+        qbuf[x] = x * 2 + static_cast<int>(q_cnt[x] & 1u);
+        mbar_wait(q_full(qbuf[x]), (q_cnt[x] >> 1) & 1u);
+        ++q_cnt[x];
+        tc_fence_after();
+        issue_qk(x, 0);
+      }
+      for (int j = 0; j < it.nmax; ++j) {
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          if (j >= it.n[x]) continue;
+          mbar_wait(p_ready(x), p_cnt[x] & 1u);
+          if (lane == 0) fa_trace(p, 1, tr_cnt, 300 + x * 10 + j);
+          ++p_cnt[x];
+          if (j == 0) mbar_wait(o_empty(x), (o_cnt[x] & 1u) ^ 1u);  // previous item's epilogue has drained O_x
+          tc_fence_after();
+          issue_pv(x, j);
+          if (j + 1 < it.n[x]) {
+            issue_qk(x, j + 1);  // in-order after PV(j): S_x / P_x is free again
+          } else {
+            if (elect_one()) umma_commit(o_full(x));
+            __syncwarp();
+            ++o_cnt[x];
+          }
+        }
+        if (elect_one()) umma_commit(kv_empty(stage_of(j)));  // every MMA that read key tile j has been issued above
+        __syncwarp();
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ------------------------------------------------------------ softmax + epilogue: one thread per query row
+    const int x = (warp_idx - 4) >> 2;   // slot
+    const int quarter = warp_idx & 3;    // TMEM lane quarter this warp may touch
+    const int row = quarter * 32 + lane;
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 128u * x;
+    const uint32_t tO = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + 128u * x;
+    const float sl2 = p.scale_log2;
+    uint32_t s_cnt = 0, o_cnt = 0;
+    unsigned int tr_cnt = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const FaItem it = fa_decode(p, item);
+      const int n_it = it.n[x];
+      if (!n_it) continue;
+      const int q0 = it.qb[x] * FA_BM;
+      const int grow = q0 + row;
+      const int wrow0 = q0 + quarter * 32;            // first query row of this warp
+      const bool warp_active = wrow0 < p.Sq;          // warps whose rows are all padding only keep the barriers moving
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_it; ++j) {
+        const int k0 = j * FA_BN;
+        int nvalid = p.Skv - k0;
+        if (nvalid > FA_BN) nvalid = FA_BN;
+        const int nch = (nvalid + 31) >> 5;           // 32-key chunks holding valid keys
+        mbar_wait(s_full(x), s_cnt & 1u);
+        ++s_cnt;
+        tc_fence_after();
+        if (quarter == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 400 + x * 10 + j);
+#ifdef VLA_FA_TRACE_BUILD
+        const int tr_role = (p.trace && blockIdx.x == 0 && quarter == 0 && lane == 0) ? 2 + x : -1;
+#else
+        constexpr int tr_role = -1;
+#endif
+        if (warp_active && !(p.debug & 1)) {
+          // causal: chunks entirely above the diagonal for every row of this warp carry no probability mass
+          int nlive = nch;
+          if (p.causal) {
+            const int lim = (wrow0 + 31 - k0) / 32 + 1;  // chunks with a key <= the warp's last row
+            nlive = lim < nch ? (lim < 0 ? 0 : lim) : nch;
+          }
+          switch (nlive) {
+            case 1: fa_softmax_tile<HD, 1>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt); break;
+            case 2: fa_softmax_tile<HD, 2>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt); break;
+            case 3: fa_softmax_tile<HD, 3>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt); break;
+            default: fa_softmax_tile<HD, 4>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt); break;
+          }
+          if (nlive < nch) {  // causal chunks above the diagonal: P = 0
+            uint32_t z[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = 0u;
+            for (int c = nlive; c < nch; ++c) tmem_st_32x32b_x16(tS + c * 16, z);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        if (quarter == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 500 + x * 10 + j);
+        mbar_arrive(p_ready(x));
+      }
+      // ---- epilogue: O / l -> bf16 -> global (each thread owns one output row of this head)
+      mbar_wait(o_full(x), o_cnt & 1u);
+      ++o_cnt;
+      tc_fence_after();
+      if (quarter == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 600 + x);
+      uint32_t o[(HD + 31) / 32][32];
+      if (warp_active) {
+#pragma unroll
+        for (int c = 0; c < (HD + 31) / 32; ++c) tmem_ld_32x32b_x32(tO + c * 32, o[c]);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty(x));  // O_x may be overwritten by the next item's first PV
+      if (warp_active && grow < p.Sq) {
+        const float inv = 1.0f / l;
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.Sq + grow) * p.ld_out + it.h[x] * HD;
+#pragma unroll
+        for (int c = 0; c < (HD + 31) / 32; ++c) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (c * 32 + q * 8 < HD) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(o[c][8 * q]) * inv, __uint_as_float(o[c][8 * q + 1]) * inv);
+              w.y = pack_bf16(__uint_as_float(o[c][8 * q + 2]) * inv, __uint_as_float(o[c][8 * q + 3]) * inv);
+              w.z = pack_bf16(__uint_as_float(o[c][8 * q + 4]) * inv, __uint_as_float(o[c][8 * q + 5]) * inv);
+              w.w = pack_bf16(__uint_as_float(o[c][8 * q + 6]) * inv, __uint_as_float(o[c][8 * q + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = w;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn fa_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// Per-head 4-D view (d, head, row, sample) of a [samples*rows, ld] bf16 matrix whose head h sits at column h*hd.
+bool make_head_map(CUtensorMap* m, const void* base, int hd, int heads, int rows, int samples, int ld, int box_d,
+                   CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = fa_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(hd), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(samples)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(hd) * 2, static_cast<cuuint64_t>(ld) * 2,
+                           static_cast<cuuint64_t>(rows) * ld * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_d), 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int fa_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Work list of one (sample, kv head): every (query head of the group, query tile) unit, heaviest first, paired
+// two by two into the slots of one work item.  Returns the number of items, or -1 if the table is too small.
+int build_items(int Sq, int Skv, int group, int causal, uint32_t* items) {
+  const int nq = (Sq + FA_BM - 1) / FA_BM, n_all = (Skv + FA_BN - 1) / FA_BN;
+  struct Unit { int h, q, cost; };
+  std::vector<Unit> units;
+  for (int q = 0; q < nq; ++q) {
+    const int rows = std::min(FA_BM, Sq - q * FA_BM);
+    const int nkv = (causal && q + 1 < n_all) ? q + 1 : n_all;
+    for (int h = 0; h < group; ++h) units.push_back({h, q, nkv * ((rows + 31) / 32)});
+  }
+  std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.cost > b.cost; });
+  const int n_items = (static_cast<int>(units.size()) + 1) / 2;
+  if (n_items > FA_MAX_ITEMS || group > 254 || nq > 255) return -1;
+  for (int i = 0; i < n_items; ++i) {
+    const Unit& a = units[2 * i];
+    uint32_t w = static_cast<uint32_t>(a.h) | (static_cast<uint32_t>(a.q) << 8);
+    if (2 * i + 1 < static_cast<int>(units.size())) {
+      const Unit& b = units[2 * i + 1];
+      w |= (static_cast<uint32_t>(b.h) << 16) | (static_cast<uint32_t>(b.q) << 24);
+    } else {
+      w |= 0xffu << 16;
+    }
+    items[i] = w;
+  }
+  return n_items;
+}
+
+template <int HD>
+int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ld_kv,
+              int Skv, int B, int n_heads, int group, int causal, __nv_bfloat16* out, int ld_out, cudaStream_t s,
+              const char** err) {
+  using L = FaSmem<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(fa_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+        cudaSuccess) {
+      if (err) *err = "attention: cudaFuncSetAttribute failed";
+      return -4;
+    }
+    attr_set = true;
+  }
+  FaDev p;
+  const int kv_heads = n_heads / group;
+  const int per_bg = build_items(Sq, Skv, group, causal, p.items);
+  if (per_bg < 0) return 1;
+  CUtensorMap mQ, mK, mV, mQt, mKt, mVt;
+  bool ok = make_head_map(&mQ, q, HD, n_heads, Sq, B, ld_q, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            make_head_map(&mK, k, HD, kv_heads, Skv, B, ld_kv, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            make_head_map(&mV, v, HD, kv_heads, Skv, B, ld_kv, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (ok && L::TAIL) {
+    ok = make_head_map(&mQt, q, HD, n_heads, Sq, B, ld_q, 16, CU_TENSOR_MAP_SWIZZLE_32B) &&
+         make_head_map(&mKt, k, HD, kv_heads, Skv, B, ld_kv, 16, CU_TENSOR_MAP_SWIZZLE_32B) &&
+         make_head_map(&mVt, v, HD, kv_heads, Skv, B, ld_kv, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+  } else if (ok) {
+    mQt = mQ;
+    mKt = mK;
+    mVt = mV;
+  }
+  if (!ok) {
+    if (err) *err = "attention: cuTensorMapEncodeTiled failed";
+    return -4;
+  }
+  p.Sq = Sq;
+  p.Skv = Skv;
+  p.group = group;
+  p.kv_heads = kv_heads;
+  p.causal = causal;
+  p.n_bg = B * kv_heads;
+  p.n_items = p.n_bg * per_bg;
+  p.scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * 1.4426950408889634f;
+  p.out = out;
+  p.ld_out = ld_out;
+  {
+    const char* dbg = getenv("VLA_FA_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  const char* trace_path = getenv("VLA_FA_TRACE");
+  p.trace = nullptr;
+  if (trace_path) {
+    cudaMalloc(&p.trace, 32004 * sizeof(unsigned int));
+    cudaMemsetAsync(p.trace, 0, 32004 * sizeof(unsigned int), s);
+  }
+  const int grid = std::min(p.n_items, fa_num_sms());
+  fa_tcgen05_kernel<HD><<<grid, FA_THREADS, L::TOTAL, s>>>(mQ, mK, mV, mQt, mKt, mVt, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = cudaGetErrorString(e);
+    return -4;
+  }
+  if (trace_path) {  // debugging aid: dump CTA 0's event log of this launch
+    std::vector<unsigned int> h(32004);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h.data(), p.trace, h.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int role = 0; role < 4; ++role) {
+        const unsigned int n = h[role] < 4000 ? h[role] : 4000;
+        for (unsigned int i = 0; i < n; ++i)
+          fprintf(f, "%d %u %u\n", role, h[4 + role * 8000 + 2 * i], h[5 + role * 8000 + 2 * i]);
+      }
+      fclose(f);
+    }
+  }
+  ops_count_launch();
+  return 0;
+}
+
+}  // namespace
+
+// Returns 1 when the shape is not served by this kernel (caller falls back to the mma.sync kernel), 0 on launch.
+int attention_tc_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                        int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal, __nv_bfloat16* out,
+                        int ld_out, cudaStream_t s, const char** err) {
+  if ((ld_out & 7) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
+  if (hd == 64) return launch_fa<64>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
+  if (hd == 72) return launch_fa<72>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
+  return 1;
+}
+
+}  // namespace vla

@@ -42,6 +42,13 @@ int cross_attention_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_
                            int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal,
                            __nv_bfloat16* out, int ld_out, cudaStream_t s, const char** err);
 
+// tcgen05/TMEM/TMA flash attention (attention_tc.cu) for hd in {64, 72}; returns 1 if the shape is not served.
+int attention_tc_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                        int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal, __nv_bfloat16* out,
+                        int ld_out, cudaStream_t s, const char** err);
+// 0 = auto (tcgen05 for hd 64/72 with Sq >= 32, mma.sync otherwise), 1 = mma.sync only, 2 = tcgen05 whenever possible
+void attention_set_impl(int impl);
+
 // Patch-embed im2col: pixel_values (B, 6*n_img, 224, 224) bf16 -> A[(b*n_img+i)*256 + p, 592]
 // with k = c*196 + ky*14 + kx (Conv2d weight order), columns 588..591 zero.  tower 0 reads channels
 // [6i, 6i+3) (DINOv2), tower 1 reads [6i+3, 6i+6) (SigLIP)  (modeling_prismatic.py:220-230).

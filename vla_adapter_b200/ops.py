@@ -87,6 +87,11 @@ def attention(qkv, B, S, n_heads, n_kv_heads, hd, causal):
     return out
 
 
+def set_attention_impl(impl: int) -> None:
+    """0 = auto, 1 = mma.sync kernel only, 2 = tcgen05 kernel whenever the head dim allows."""
+    _lib.check(_lib.load().vla_set_attention_impl(int(impl)))
+
+
 def rope_(x, off, n_heads, B, S, theta):
     _need_cuda(x)
     _lib.check(_lib.load().vla_op_rope(_ptr(x), x.stride(0), off, n_heads, B, S, float(theta), _stream()))
