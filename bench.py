@@ -252,7 +252,9 @@ def main():
         e1.record()
         sync_all()
     ms_step = reduce_max(e0.elapsed_time(e1) / K)
-    launches = lib.vla_total_launch_count() - launches0
+    # kernels launched inside the timed region: the engine replays a captured CUDA graph of its forward, so the
+    # per-step count is the one recorded at capture time (vla_last_launch_count), not a host-side counter delta
+    launches = max(lib.vla_total_launch_count() - launches0, eng.last_launch_count() * K)
     value = world * B / (ms_step * 1e-3)
     assert torch.isfinite(out).all(), "non-finite action chunk"
 

@@ -11,6 +11,7 @@
 #include "ops.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -122,6 +123,28 @@ struct vla_engine {
   // last call
   int lastB = 0, lastL = 0;
   long long last_launches = 0;
+
+  // CUDA graphs of forward(): one per distinct (B, L, buffer pointers), captured on the second call with that
+  // key (the first runs eagerly and performs the one-time cudaFuncSetAttribute calls).  Replayed on an internal
+  // stream fenced to the caller's stream with events, so the legacy default stream works too.
+  struct GraphKey {
+    int B, L;
+    const void *pix, *ids, *aq, *prop, *out_norm, *out_unnorm, *out_ha;
+    bool operator==(const GraphKey& o) const {
+      return B == o.B && L == o.L && pix == o.pix && ids == o.ids && aq == o.aq && prop == o.prop &&
+             out_norm == o.out_norm && out_unnorm == o.out_unnorm && out_ha == o.out_ha;
+    }
+  };
+  struct GraphEntry {
+    GraphKey key;
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t gev_in = nullptr, gev_out = nullptr;
+  int use_graphs = 1;
 
   int fail(int code, const std::string& m) {
     err = m;
@@ -432,6 +455,7 @@ int vla_create(const vla_cfg* cfg, vla_engine** out) {
   vla_engine* e = new vla_engine();
   e->cfg = *cfg;
   *out = e;
+  if (const char* ng = getenv("VLA_NO_GRAPH")) e->use_graphs = atoi(ng) ? 0 : 1;
   const vla_cfg& c = e->cfg;
   if (c.n_images < 1 || c.n_images > 3) return e->fail(VLA_ERR_INVALID, "n_images must be 1..3");
   if (c.chunk_len < 1 || c.chunk_len > 32) return e->fail(VLA_ERR_INVALID, "chunk_len must be 1..32");
@@ -692,10 +716,62 @@ int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
     return e->fail(VLA_ERR_INVALID, "vla_predict: null input/output pointer");
   if (B < 1 || B > e->maxB) return e->fail(VLA_ERR_INVALID, "vla_predict: batch outside [1, max_batch]");
   if (L < 1 || L > e->maxL) return e->fail(VLA_ERR_INVALID, "vla_predict: prompt length outside [1, max_prompt_len]");
-  const long long before = vla::gemm_launch_count() + vla::ops_launch_count();
-  int rc = forward(e, static_cast<const bf16*>(pixel_values), ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm,
-                   static_cast<bf16*>(out_last_ha), static_cast<cudaStream_t>(stream));
-  e->last_launches = vla::gemm_launch_count() + vla::ops_launch_count() - before;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bf16* pix = static_cast<const bf16*>(pixel_values);
+  bf16* ha = static_cast<bf16*>(out_last_ha);
+  int rc = 0;
+  vla_engine::GraphEntry* ge = nullptr;
+  if (e->use_graphs && !vla::gemm_profile_enabled()) {
+    const vla_engine::GraphKey key{B, L, pixel_values, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha};
+    for (auto& g : e->graphs)
+      if (g.key == key) ge = &g;
+    if (!ge) {
+      if (e->graphs.size() >= 16) {  // bounded cache: drop the oldest entry
+        if (e->graphs.front().exec) cudaGraphExecDestroy(e->graphs.front().exec);
+        e->graphs.erase(e->graphs.begin());
+      }
+      e->graphs.push_back(vla_engine::GraphEntry());
+      ge = &e->graphs.back();
+      ge->key = key;
+    }
+    ++ge->seen;
+  }
+  if (ge && ge->seen >= 2) {
+    if (!e->gstream) {
+      if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->gev_in, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->gev_out, cudaEventDisableTiming) != cudaSuccess)
+        return e->fail(VLA_ERR_CUDA, "graph stream/event creation failed");
+    }
+    if (!ge->exec) {
+      cudaGraph_t graph = nullptr;
+      const long long before = vla::gemm_launch_count() + vla::ops_launch_count();
+      if (cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+        return e->fail(VLA_ERR_CUDA, "cudaStreamBeginCapture failed");
+      rc = forward(e, pix, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, ha, e->gstream);
+      const cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
+      ge->launches = vla::gemm_launch_count() + vla::ops_launch_count() - before;
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (ce != cudaSuccess || !graph) return e->fail(VLA_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+      const cudaError_t ci = cudaGraphInstantiate(&ge->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ci != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ci));
+    }
+    cudaError_t ce = cudaEventRecord(e->gev_in, s);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->gstream, e->gev_in, 0);
+    if (ce == cudaSuccess) ce = cudaGraphLaunch(ge->exec, e->gstream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e->gev_out, e->gstream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, e->gev_out, 0);
+    if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("graph launch: ") + cudaGetErrorString(ce));
+    e->last_launches = ge->launches;
+  } else {
+    const long long before = vla::gemm_launch_count() + vla::ops_launch_count();
+    rc = forward(e, pix, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, ha, s);
+    e->last_launches = vla::gemm_launch_count() + vla::ops_launch_count() - before;
+  }
   e->lastB = B;
   e->lastL = L;
   return rc;
@@ -800,6 +876,11 @@ const char* vla_last_error(const vla_engine* e) { return e ? e->err.c_str() : "n
 void vla_destroy(vla_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
+  for (auto& g : e->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (e->gev_in) cudaEventDestroy(e->gev_in);
+  if (e->gev_out) cudaEventDestroy(e->gev_out);
+  if (e->gstream) cudaStreamDestroy(e->gstream);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
 }

@@ -387,6 +387,8 @@ int num_sms() {
 
 long long gemm_launch_count() { return g_launches.load(); }
 
+bool gemm_profile_enabled() { return g_prof_on; }
+
 void gemm_profile_enable(bool on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = on;

@@ -48,6 +48,7 @@ long long gemm_launch_count();
 
 // Per-launch CUDA-event timing of the GEMM kernel (bench.py roofline leg).
 void gemm_profile_enable(bool on);
+bool gemm_profile_enabled();
 int gemm_profile_read(double* total_ms, long long* launches);
 
 }  // namespace vla

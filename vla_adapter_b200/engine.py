@@ -38,6 +38,7 @@ class VLAEngine:
         if not torch.cuda.is_available():
             raise RuntimeError("VLAEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
+        self._out_bufs = {}
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         torch.cuda.set_device(self.device)
         self.n_images, self.chunk_len, self.action_dim, self.proprio_dim = n_images, chunk_len, action_dim, proprio_dim
@@ -176,15 +177,23 @@ class VLAEngine:
         assert pixel_values.dtype == torch.bfloat16 and pixel_values.is_contiguous()
         if tuple(pixel_values.shape) != (B, 6 * self.n_images, 224, 224):
             raise ValueError(f"pixel_values must be ({B}, {6 * self.n_images}, 224, 224), got {tuple(pixel_values.shape)}")
-        out_n = torch.empty((B, T, A), dtype=torch.float32, device=self.device)
-        out_u = torch.empty((B, T, A), dtype=torch.float32, device=self.device)
-        ha = torch.empty((B, NUM_TOKENS, LLM_DIM), dtype=torch.bfloat16, device=self.device) if want_last_ha else None
+        # The engine replays a CUDA graph keyed on (B, L, buffer addresses): write into buffers that stay put and
+        # hand fresh copies (a few hundred bytes per sample) to the caller.
+        key = (B, want_last_ha)
+        bufs = self._out_bufs.get(key)
+        if bufs is None:
+            bufs = (torch.empty((B, T, A), dtype=torch.float32, device=self.device),
+                    torch.empty((B, T, A), dtype=torch.float32, device=self.device),
+                    torch.empty((B, NUM_TOKENS, LLM_DIM), dtype=torch.bfloat16, device=self.device)
+                    if want_last_ha else None)
+            self._out_bufs[key] = bufs
+        out_n, out_u, ha = bufs
         rc = self.lib.vla_predict(self._h, pixel_values.data_ptr(), ext_ids.data_ptr(), aq_index.data_ptr(),
                                   proprio.data_ptr(), B, L, out_n.data_ptr(), out_u.data_ptr(),
                                   ha.data_ptr() if ha is not None else None,
                                   torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, self._h)
-        return out_n, out_u, ha
+        return out_n.clone(), out_u.clone(), (ha.clone() if ha is not None else None)
 
     def predict_host(self, pixel_values: torch.Tensor, ext_ids: torch.Tensor, aq_index: torch.Tensor,
                      proprio: torch.Tensor, out_norm: torch.Tensor, out_unnorm: torch.Tensor,
