@@ -1,7 +1,7 @@
 #!/bin/bash
 # tcgen05 attention check: parity tests under a timeout (a deadlock must not eat the budget), then timings.
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_ops_gpu.py -q -x -k "attention" > gpurun_out/attn_all.log 2>&1
+timeout 120 python -m pytest tests/test_ops_gpu.py -q -x -k "attention" > gpurun_out/attn_all.log 2>&1
 rc=$?
 echo "attn_all rc=$rc"
 tail -30 gpurun_out/attn_all.log

@@ -18,7 +18,10 @@
 //                              fp32 score row, mask, running max with lazy rescaling of O (only when the max grows
 //                              by > 2^8), exp2, row sum, P -> bf16 -> tcgen05.st over the score columns; finally
 //                              O / l -> bf16 -> global.
-// TMEM columns: [0,128) S_A (P_A aliases [0,64)), [128,256) S_B, [256,256+hd) O_A, [384,384+hd) O_B.
+// Two configurations: head dim 64 uses 64-key tiles and 256 TMEM columns so that TWO CTAs (four slots) share an SM -
+// each slot's QK -> softmax -> PV chain is latency-bound, four chains keep the MUFU and the tensor pipe busy; head
+// dim 72 needs 2*80 accumulator columns and runs 128-key tiles with one CTA per SM.
+// TMEM columns: S_A [0,BN) (P_A aliases its first half), S_B [BN,2BN), then O_A, O_B.
 //
 // Head dim 72 is handled as a 64-wide main block (128B-swizzled tiles) plus a 16-wide tail block
 // (32B-swizzled tiles) whose columns 72..79 are zero-filled by TMA: the tensor maps are per-head 4-D views
@@ -37,15 +40,14 @@ namespace vla {
 namespace {
 
 constexpr int FA_BM = 128;
-constexpr int FA_BN = 128;
 constexpr int FA_THREADS = 384;  // warpgroup 0: TMA + MMA warps (+2 idle), warpgroups 1/2: softmax of slot A/B
-constexpr uint32_t FA_TMEM_COLS = 512;
-constexpr uint32_t FA_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr uint32_t FA_TAIL_BYTES = 128 * 32;   // 128 rows x 16 bf16
+constexpr uint32_t FA_TILE_BYTES = 128 * 128;  // Q tile: 128 rows x 64 bf16
+constexpr uint32_t FA_TAIL_BYTES = 128 * 32;   // Q tail: 128 rows x 16 bf16
 constexpr int FA_MAX_ITEMS = 24;               // work items per (sample, kv head)
 
 struct FaDev {
   int Sq, Skv, group, kv_heads, causal;
+  int bn;       // keys per tile (64: two CTAs per SM, 128: one)
   int n_bg;     // samples * kv heads
   int n_items;  // n_bg * items per (sample, kv head)
   float scale_log2;
@@ -85,13 +87,14 @@ VLA_DEVINL FaItem fa_decode(const FaDev& p, int item) {
   it.b = bg / p.kv_heads;
   it.g = bg - it.b * p.kv_heads;
   const uint32_t w = p.items[r];
-  const int n_all = (p.Skv + FA_BN - 1) / FA_BN;
+  const int n_all = (p.Skv + p.bn - 1) / p.bn;
 #pragma unroll
   for (int x = 0; x < 2; ++x) {
     const int hr = (w >> (16 * x)) & 0xff, q = (w >> (16 * x + 8)) & 0xff;
     it.h[x] = it.g * p.group + hr;
     it.qb[x] = q;
-    it.n[x] = hr == 0xff ? 0 : ((p.causal && q + 1 < n_all) ? q + 1 : n_all);
+    const int n_c = ((q + 1) * FA_BM + p.bn - 1) / p.bn;  // causal: key tiles up to this query tile's last row
+    it.n[x] = hr == 0xff ? 0 : ((p.causal && n_c < n_all) ? n_c : n_all);
   }
   it.nmax = it.n[0] > it.n[1] ? it.n[0] : it.n[1];
   return it;
@@ -149,6 +152,17 @@ VLA_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
       "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+VLA_DEVINL void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+VLA_DEVINL void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 VLA_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 VLA_DEVINL float ex2f(float x) {
@@ -159,7 +173,7 @@ VLA_DEVINL float ex2f(float x) {
 
 // Softmax of one 128-row x (NLIVE*32)-key score tile for this thread's query row: scores from TMEM, mask, running
 // max with lazy O rescale, exp2, row sum, P (bf16) back over the score columns.
-template <int HD, int NLIVE>
+template <int HD, int NLIVE, bool MASKED>
 VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tS, uint32_t tO, int k0, int wrow0, int grow, int j, float sl2,
                                 float& m_ref, float& l, int tr_role, unsigned int& tr_cnt) {
 #ifdef VLA_FA_TRACE_BUILD
@@ -172,17 +186,14 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tS, uint32_t tO, int k0
   for (int c = 0; c < NLIVE; ++c) tmem_ld_32x32b_x32(tS + c * 32, v[c]);
   tmem_ld_wait();
   if (tr) fa_trace(p, tr_role, tr_cnt, 700);
+  if (MASKED) {  // tile touches the causal diagonal or the end of the keys: straight-line select on every element
+    int last = p.Skv - 1;                        // last key this row may attend to ...
+    if (p.causal && grow < last) last = grow;
+    last -= k0;                                  // ... relative to this tile
 #pragma unroll
-  for (int c = 0; c < NLIVE; ++c) {
-    const int c0 = k0 + c * 32;
-    if (c0 + 32 > p.Skv || (p.causal && c0 + 31 > wrow0)) {  // warp-uniform: chunk touches the diagonal or the tail
-      int last = p.Skv - 1;                      // last key this row may attend to ...
-      if (p.causal && grow < last) last = grow;
-      last -= c0;                                // ... relative to this chunk
+    for (int c = 0; c < NLIVE; ++c)
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i > last) v[c][i] = 0xff800000u;     // -inf
-    }
+      for (int i = 0; i < 32; ++i) v[c][i] = (c * 32 + i > last) ? 0xff800000u : v[c][i];  // -inf
   }
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -206,14 +217,15 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tS, uint32_t tO, int k0
       if (need) m_ref = m_new;
       l *= alpha;
       // s_full(j) was committed after PV(j-1), so O is stable here and PV(j) has not been issued yet.
+      // (rare path: 8 columns at a time keeps its register footprint out of the hot loop's allocation)
 #pragma unroll 1
-      for (int c = 0; c < (HD + 31) / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tO + c * 32, o);
+      for (int c = 0; c < (HD + 7) / 8; ++c) {
+        uint32_t o[8];
+        tmem_ld_32x32b_x8(tO + c * 8, o);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32b_x32(tO + c * 32, o);
+        for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32b_x8(tO + c * 8, o);
       }
     }
   }
@@ -247,35 +259,43 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tS, uint32_t tO, int k0
   l += s0 + s1;
 }
 
-template <int HD>
+template <int HD, int BN>
 struct FaSmem {
   static constexpr bool TAIL = HD > 64;
-  static constexpr int STAGES = TAIL ? 3 : 4;
+  static constexpr int CTAS_PER_SM = BN == 64 ? 2 : 1;
+  static constexpr int STAGES = 3;
   static constexpr int QBUFS = 4;  // 2 slots x 2 buffers: the next item's Q tiles land while this item computes
+  static constexpr uint32_t KV_TILE = BN * 128;  // BN keys x 64 bf16
+  static constexpr uint32_t KV_TAIL = BN * 32;   // BN keys x 16 bf16
   static constexpr uint32_t Q_BYTES = FA_TILE_BYTES + (TAIL ? FA_TAIL_BYTES : 0);
-  static constexpr uint32_t KV_BYTES = 2 * FA_TILE_BYTES + (TAIL ? 2 * FA_TAIL_BYTES : 0);
+  static constexpr uint32_t KV_BYTES = 2 * KV_TILE + (TAIL ? 2 * KV_TAIL : 0);
   // main tiles first (1024-byte aligned), then the 32B-swizzled tails, then barriers
   static constexpr uint32_t OFF_Q = 0;                               // QBUFS
   static constexpr uint32_t OFF_K = QBUFS * FA_TILE_BYTES;           // STAGES
-  static constexpr uint32_t OFF_V = OFF_K + STAGES * FA_TILE_BYTES;  // STAGES
-  static constexpr uint32_t OFF_QT = OFF_V + STAGES * FA_TILE_BYTES;
+  static constexpr uint32_t OFF_V = OFF_K + STAGES * KV_TILE;        // STAGES
+  static constexpr uint32_t OFF_QT = OFF_V + STAGES * KV_TILE;
   static constexpr uint32_t OFF_KT = OFF_QT + QBUFS * FA_TAIL_BYTES;
-  static constexpr uint32_t OFF_VT = OFF_KT + STAGES * FA_TAIL_BYTES;
-  static constexpr uint32_t OFF_BAR = TAIL ? OFF_VT + STAGES * FA_TAIL_BYTES : OFF_QT;
-  static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024 /*align slack*/;
+  static constexpr uint32_t OFF_VT = OFF_KT + STAGES * KV_TAIL;
+  static constexpr uint32_t OFF_BAR = TAIL ? OFF_VT + STAGES * KV_TAIL : OFF_QT;
+  static constexpr uint32_t TOTAL = OFF_BAR + 256;  // the dynamic array is declared __align__(1024): no slack needed
+  // TMEM columns: S_A [0,BN), S_B [BN,2BN) (P aliases the first half of S), then O_A, O_B
+  static constexpr uint32_t O_OFF = 2 * BN;
+  static constexpr uint32_t O_STRIDE = TAIL ? 128 : 64;
+  static constexpr uint32_t TMEM_COLS = BN == 64 ? 256 : 512;
+  static_assert(!(TAIL && BN == 64), "head dim 72 needs 2*64 + 2*80 TMEM columns: use BN = 128");
 };
 
-template <int HD>
-__global__ void __launch_bounds__(FA_THREADS, 1)
+template <int HD, int BN>
+__global__ void __launch_bounds__(FA_THREADS, (FaSmem<HD, BN>::CTAS_PER_SM))
 fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                   const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapQt,
                   const __grid_constant__ CUtensorMap mapKt, const __grid_constant__ CUtensorMap mapVt,
                   const __grid_constant__ FaDev p) {
-  using L = FaSmem<HD>;
+  using L = FaSmem<HD, BN>;
   constexpr bool TAIL = L::TAIL;
   constexpr int NS = L::STAGES;
 
-  extern __shared__ uint8_t fa_smem_raw[];
+  extern __shared__ __align__(1024) uint8_t fa_smem_raw[];
   const uint32_t raw_addr = smem_u32(fa_smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* smem = fa_smem_raw + pad;
@@ -318,7 +338,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     fence_proxy_async();
   }
   if (warp_idx == 1) {
-    tmem_alloc(smem_u32(tmem_slot), FA_TMEM_COLS);
+    tmem_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
     tmem_relinquish();
     tc_fence_before();
   }
@@ -327,7 +347,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp_idx < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (BN == 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp_idx == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp waits, one lane issues)
     uint32_t kv_cnt = 0, q_cnt[2] = {0, 0};
@@ -356,11 +377,11 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         if (elect_one()) {
           fa_trace(p, 0, tr_cnt, 100 + j);
           mbar_arrive_expect_tx(kv_full(s), L::KV_BYTES);
-          tma_load_4d(sbase + L::OFF_K + s * FA_TILE_BYTES, &mapK, kv_full(s), 0, it.g, j * FA_BN, it.b);
-          tma_load_4d(sbase + L::OFF_V + s * FA_TILE_BYTES, &mapV, kv_full(s), 0, it.g, j * FA_BN, it.b);
+          tma_load_4d(sbase + L::OFF_K + s * L::KV_TILE, &mapK, kv_full(s), 0, it.g, j * BN, it.b);
+          tma_load_4d(sbase + L::OFF_V + s * L::KV_TILE, &mapV, kv_full(s), 0, it.g, j * BN, it.b);
           if (TAIL) {
-            tma_load_4d(sbase + L::OFF_KT + s * FA_TAIL_BYTES, &mapKt, kv_full(s), 64, it.g, j * FA_BN, it.b);
-            tma_load_4d(sbase + L::OFF_VT + s * FA_TAIL_BYTES, &mapVt, kv_full(s), 64, it.g, j * FA_BN, it.b);
+            tma_load_4d(sbase + L::OFF_KT + s * L::KV_TAIL, &mapKt, kv_full(s), 64, it.g, j * BN, it.b);
+            tma_load_4d(sbase + L::OFF_VT + s * L::KV_TAIL, &mapVt, kv_full(s), 64, it.g, j * BN, it.b);
           }
         }
         __syncwarp();
@@ -387,8 +408,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         tc_fence_after();
       };
       auto n16_of = [&](int j) {
-        int nvalid = p.Skv - j * FA_BN;
-        if (nvalid > FA_BN) nvalid = FA_BN;
+        int nvalid = p.Skv - j * BN;
+        if (nvalid > BN) nvalid = BN;
         return (nvalid + 15) >> 4;  // key columns actually computed, in units of 16
       };
       int qbuf[2] = {0, 0};
@@ -396,9 +417,9 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       auto issue_qk = [&](int x, int j) {
         need_kv(j);
         const int s = stage_of(j);
-        const uint32_t tS = tmem_base + 128u * x;
+        const uint32_t tS = tmem_base + static_cast<uint32_t>(BN) * x;
         const uint32_t idesc_qk = make_idesc_bf16(128, static_cast<uint32_t>(n16_of(j) * 16));
-        const uint32_t sq = sbase + L::OFF_Q + qbuf[x] * FA_TILE_BYTES, sk = sbase + L::OFF_K + s * FA_TILE_BYTES;
+        const uint32_t sq = sbase + L::OFF_Q + qbuf[x] * FA_TILE_BYTES, sk = sbase + L::OFF_K + s * L::KV_TILE;
         if (elect_one()) {
           if (!(p.debug & 4)) {
 #pragma unroll
@@ -407,7 +428,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                         make_smem_desc(sk + k * 32, 1024, LAYOUT_SW128), idesc_qk, k != 0 ? 1u : 0u);
             if (TAIL)
               umma_bf16(tS, make_smem_desc(sbase + L::OFF_QT + qbuf[x] * FA_TAIL_BYTES, 256, LAYOUT_SW32),
-                        make_smem_desc(sbase + L::OFF_KT + s * FA_TAIL_BYTES, 256, LAYOUT_SW32), idesc_qk, 1u);
+                        make_smem_desc(sbase + L::OFF_KT + s * L::KV_TAIL, 256, LAYOUT_SW32), idesc_qk, 1u);
           }
           umma_commit(s_full(x));
           if (j == it.n[x] - 1) umma_commit(q_empty(qbuf[x]));  // last use of this Q tile
@@ -418,15 +439,15 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       auto issue_pv = [&](int x, int j) {
         const int s = stage_of(j);
         const int n16 = n16_of(j);
-        const uint32_t tS = tmem_base + 128u * x, tO = tmem_base + 256u + 128u * x;
-        const uint32_t sv = sbase + L::OFF_V + s * FA_TILE_BYTES;
+        const uint32_t tS = tmem_base + static_cast<uint32_t>(BN) * x, tO = tmem_base + L::O_OFF + L::O_STRIDE * x;
+        const uint32_t sv = sbase + L::OFF_V + s * L::KV_TILE;
         if (elect_one()) {
           if (!(p.debug & 2)) {
             for (int kk = 0; kk < n16; ++kk)
               umma_bf16_ts(tO, tS + kk * 8, make_smem_desc(sv + kk * 2048, 1024, LAYOUT_SW128), idesc_pv,
                            (j | kk) != 0 ? 1u : 0u);
             if (TAIL) {
-              const uint32_t svt = sbase + L::OFF_VT + s * FA_TAIL_BYTES;
+              const uint32_t svt = sbase + L::OFF_VT + s * L::KV_TAIL;
               for (int kk = 0; kk < n16; ++kk)
                 umma_bf16_ts(tO + 64, tS + kk * 8, make_smem_desc(svt + kk * 512, 256, LAYOUT_SW32), idesc_pvt,
                              (j | kk) != 0 ? 1u : 0u);
@@ -468,13 +489,14 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if (BN == 64) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 128*32 + 256*104 == 384*80 (launch allocation)
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ------------------------------------------------------------ softmax + epilogue: one thread per query row
     const int x = (warp_idx - 4) >> 2;   // slot
     const int quarter = warp_idx & 3;    // TMEM lane quarter this warp may touch
     const int row = quarter * 32 + lane;
-    const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 128u * x;
-    const uint32_t tO = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + 128u * x;
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(BN) * x;
+    const uint32_t tO = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + L::O_OFF + L::O_STRIDE * x;
     const float sl2 = p.scale_log2;
     uint32_t s_cnt = 0, o_cnt = 0;
     unsigned int tr_cnt = 0;
@@ -488,9 +510,9 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       const bool warp_active = wrow0 < p.Sq;          // warps whose rows are all padding only keep the barriers moving
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < n_it; ++j) {
-        const int k0 = j * FA_BN;
+        const int k0 = j * BN;
         int nvalid = p.Skv - k0;
-        if (nvalid > FA_BN) nvalid = FA_BN;
+        if (nvalid > BN) nvalid = BN;
         const int nch = (nvalid + 31) >> 5;           // 32-key chunks holding valid keys
         mbar_wait(s_full(x), s_cnt & 1u);
         ++s_cnt;
@@ -508,11 +530,24 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             const int lim = (wrow0 + 31 - k0) / 32 + 1;  // chunks with a key <= the warp's last row
             nlive = lim < nch ? (lim < 0 ? 0 : lim) : nch;
           }
-          switch (nlive) {
-            case 1: fa_softmax_tile<HD, 1>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt); break;
-            case 2: fa_softmax_tile<HD, 2>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt); break;
-            case 3: fa_softmax_tile<HD, 3>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt); break;
-            default: fa_softmax_tile<HD, 4>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt); break;
+          // warp-uniform: does any live chunk touch the causal diagonal or the end of the keys?
+          const bool masked = (k0 + nlive * 32 > p.Skv) || (p.causal && k0 + nlive * 32 - 1 > wrow0);
+          if constexpr (BN == 64) {
+            if (nlive == 1) (masked ? fa_softmax_tile<HD, 1, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
+                    : fa_softmax_tile<HD, 1, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt));
+            else (masked ? fa_softmax_tile<HD, 2, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
+                    : fa_softmax_tile<HD, 2, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt));
+          } else {
+            switch (nlive) {
+              case 1: (masked ? fa_softmax_tile<HD, 1, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
+                    : fa_softmax_tile<HD, 1, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)); break;
+              case 2: (masked ? fa_softmax_tile<HD, 2, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
+                    : fa_softmax_tile<HD, 2, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)); break;
+              case 3: (masked ? fa_softmax_tile<HD, 3, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
+                    : fa_softmax_tile<HD, 3, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)); break;
+              default: (masked ? fa_softmax_tile<HD, 4, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
+                    : fa_softmax_tile<HD, 4, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)); break;
+            }
           }
           if (nlive < nch) {  // causal chunks above the diagonal: P = 0
             uint32_t z[16];
@@ -564,7 +599,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
@@ -588,14 +623,14 @@ EncodeTiledFn fa_encode_fn() {
 
 // Per-head 4-D view (d, head, row, sample) of a [samples*rows, ld] bf16 matrix whose head h sits at column h*hd.
 bool make_head_map(CUtensorMap* m, const void* base, int hd, int heads, int rows, int samples, int ld, int box_d,
-                   CUtensorMapSwizzle swz) {
+                   int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = fa_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(hd), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(rows),
                         static_cast<cuuint64_t>(samples)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(hd) * 2, static_cast<cuuint64_t>(ld) * 2,
                            static_cast<cuuint64_t>(rows) * ld * 2};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_d), 1, 128, 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_d), 1, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -615,13 +650,14 @@ int fa_num_sms() {
 
 // Work list of one (sample, kv head): every (query head of the group, query tile) unit, heaviest first, paired
 // two by two into the slots of one work item.  Returns the number of items, or -1 if the table is too small.
-int build_items(int Sq, int Skv, int group, int causal, uint32_t* items) {
-  const int nq = (Sq + FA_BM - 1) / FA_BM, n_all = (Skv + FA_BN - 1) / FA_BN;
+int build_items(int Sq, int Skv, int group, int causal, int bn, uint32_t* items) {
+  const int nq = (Sq + FA_BM - 1) / FA_BM, n_all = (Skv + bn - 1) / bn;
   struct Unit { int h, q, cost; };
   std::vector<Unit> units;
   for (int q = 0; q < nq; ++q) {
     const int rows = std::min(FA_BM, Sq - q * FA_BM);
-    const int nkv = (causal && q + 1 < n_all) ? q + 1 : n_all;
+    const int n_c = ((q + 1) * FA_BM + bn - 1) / bn;
+    const int nkv = (causal && n_c < n_all) ? n_c : n_all;
     for (int h = 0; h < group; ++h) units.push_back({h, q, nkv * ((rows + 31) / 32)});
   }
   std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.cost > b.cost; });
@@ -641,14 +677,14 @@ int build_items(int Sq, int Skv, int group, int causal, uint32_t* items) {
   return n_items;
 }
 
-template <int HD>
+template <int HD, int BN>
 int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ld_kv,
               int Skv, int B, int n_heads, int group, int causal, __nv_bfloat16* out, int ld_out, cudaStream_t s,
               const char** err) {
-  using L = FaSmem<HD>;
+  using L = FaSmem<HD, BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(fa_tcgen05_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+    if (cudaFuncSetAttribute(fa_tcgen05_kernel<HD, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
         cudaSuccess) {
       if (err) *err = "attention: cudaFuncSetAttribute failed";
       return -4;
@@ -657,16 +693,16 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
   }
   FaDev p;
   const int kv_heads = n_heads / group;
-  const int per_bg = build_items(Sq, Skv, group, causal, p.items);
+  const int per_bg = build_items(Sq, Skv, group, causal, BN, p.items);
   if (per_bg < 0) return 1;
   CUtensorMap mQ, mK, mV, mQt, mKt, mVt;
-  bool ok = make_head_map(&mQ, q, HD, n_heads, Sq, B, ld_q, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
-            make_head_map(&mK, k, HD, kv_heads, Skv, B, ld_kv, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
-            make_head_map(&mV, v, HD, kv_heads, Skv, B, ld_kv, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  bool ok = make_head_map(&mQ, q, HD, n_heads, Sq, B, ld_q, 64, FA_BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            make_head_map(&mK, k, HD, kv_heads, Skv, B, ld_kv, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            make_head_map(&mV, v, HD, kv_heads, Skv, B, ld_kv, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (ok && L::TAIL) {
-    ok = make_head_map(&mQt, q, HD, n_heads, Sq, B, ld_q, 16, CU_TENSOR_MAP_SWIZZLE_32B) &&
-         make_head_map(&mKt, k, HD, kv_heads, Skv, B, ld_kv, 16, CU_TENSOR_MAP_SWIZZLE_32B) &&
-         make_head_map(&mVt, v, HD, kv_heads, Skv, B, ld_kv, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+    ok = make_head_map(&mQt, q, HD, n_heads, Sq, B, ld_q, 16, FA_BM, CU_TENSOR_MAP_SWIZZLE_32B) &&
+         make_head_map(&mKt, k, HD, kv_heads, Skv, B, ld_kv, 16, BN, CU_TENSOR_MAP_SWIZZLE_32B) &&
+         make_head_map(&mVt, v, HD, kv_heads, Skv, B, ld_kv, 16, BN, CU_TENSOR_MAP_SWIZZLE_32B);
   } else if (ok) {
     mQt = mQ;
     mKt = mK;
@@ -676,6 +712,7 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
     if (err) *err = "attention: cuTensorMapEncodeTiled failed";
     return -4;
   }
+  p.bn = BN;
   p.Sq = Sq;
   p.Skv = Skv;
   p.group = group;
@@ -696,8 +733,8 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
     cudaMalloc(&p.trace, 32004 * sizeof(unsigned int));
     cudaMemsetAsync(p.trace, 0, 32004 * sizeof(unsigned int), s);
   }
-  const int grid = std::min(p.n_items, fa_num_sms());
-  fa_tcgen05_kernel<HD><<<grid, FA_THREADS, L::TOTAL, s>>>(mQ, mK, mV, mQt, mKt, mVt, p);
+  const int grid = std::min(p.n_items, L::CTAS_PER_SM * fa_num_sms());
+  fa_tcgen05_kernel<HD, BN><<<grid, FA_THREADS, L::TOTAL, s>>>(mQ, mK, mV, mQt, mKt, mVt, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = cudaGetErrorString(e);
@@ -728,8 +765,8 @@ int attention_tc_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfl
                         int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal, __nv_bfloat16* out,
                         int ld_out, cudaStream_t s, const char** err) {
   if ((ld_out & 7) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
-  if (hd == 64) return launch_fa<64>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
-  if (hd == 72) return launch_fa<72>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
+  if (hd == 64) return launch_fa<64, 128>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
+  if (hd == 72) return launch_fa<72, 128>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
   return 1;
 }
 
