@@ -67,6 +67,49 @@ def test_engine_matches_oracle(pro, n_images, B, L):
         2 * _rel(ref16["last_ha"].reshape(-1), truth["last_ha"].reshape(-1)), 1e-2)
 
 
+@pytest.mark.parametrize("pro", [False, True])
+def test_engine_aloha_shaped_chunk(pro):
+    """The larger-chunk preset of the reference (ALOHA constants, prismatic/vla/constants.py:42-47: 25 x 14 chunk,
+    14-d proprio; fc1 input 14*896) - BASELINE.json configs[4] asks for the Pro head at a larger action chunk."""
+    cfg, truth, ref16, normalized, actions, ha, got, launches = _run_case(pro, 2, 2, 24, seed=5, T=25, A=14, P=14)
+    assert normalized.shape == (2, 25, 14)
+    tn = truth["normalized"].numpy()
+    e_ref = np.abs(ref16["normalized"].numpy() - tn)
+    e_eng = np.abs(normalized - tn)
+    print(f"aloha pro={pro}: engine max {e_eng.max():.4f} mean {e_eng.mean():.4f} | ref_bf16 max {e_ref.max():.4f} mean {e_ref.mean():.4f}")
+    assert e_eng.max() <= max(2 * e_ref.max(), 2e-2)
+    assert e_eng.mean() <= 5e-3 + e_ref.mean()
+    for k in ("head_x.1", "head_x.24"):
+        t = truth[k].float().reshape(-1)
+        assert _rel(got[k].float(), t) <= max(2 * _rel(ref16[k].reshape(-1), t), 1e-2), k
+
+
+def test_engine_graph_replay_is_deterministic():
+    """Calls 2+ with the same shapes and buffers replay a captured CUDA graph of the forward: results must be
+    bit-identical to the eager first call, and different inputs through the same graph must change the output."""
+    from vla_adapter_b200.engine import VLAEngine
+
+    cfg = O.OracleConfig(n_images=2, dino_depth=3, siglip_depth=3, vocab_size=2048, pro=False)
+    W = O.make_weights(cfg, seed=1)
+    pix, ids, prop = O.make_inputs(cfg, 2, 19, seed=1)
+    eng = VLAEngine(n_images=2, dino_depth=3, siglip_depth=3, vocab_size=2048, max_batch=2, max_prompt_len=19)
+    eng.load_flat(W)
+    eng.finalize()
+    ext, aq = eng._prep(ids, None)
+    dev = eng.device
+    pix_d, ext_d, aq_d, prop_d = pix.to(dev).to(torch.bfloat16).contiguous(), ext.to(dev), aq.to(dev), prop.to(dev).float()
+    outs = [eng.predict_device(pix_d, ext_d, aq_d, prop_d)[0].cpu() for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    n_eager = eng.last_launch_count()
+    assert n_eager > 100
+    pix_d.mul_(0.5)   # same buffers, new contents: the replayed graph must see them
+    changed = eng.predict_device(pix_d, ext_d, aq_d, prop_d)[0].cpu()
+    assert eng.last_launch_count() == n_eager
+    eng.close()
+    assert not torch.equal(changed, outs[0])
+
+
 def test_base_rows_identical_and_causal_invariants():
     """Reference properties: base head has no positional signal, so all T rows agree."""
     cfg, truth, ref16, normalized, actions, ha, got, _ = _run_case(False, 2, 2, 17, seed=3)

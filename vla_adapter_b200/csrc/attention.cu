@@ -6,6 +6,7 @@
 // fp32, cp.async double-buffered K/V) on warp-level mma.sync.m16n8k16 bf16 tensor-core tiles.
 // Attention is ~4 % of the path's FLOPs; the tcgen05 GEMM carries the other 96 %.
 #include "common.cuh"
+#include "launch.cuh"
 #include "ops.cuh"
 
 namespace vla {
@@ -49,6 +50,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
 flash_attn_kernel(const __nv_bfloat16* __restrict__ qp, int ld_q, int Sq, const __nv_bfloat16* __restrict__ kp,
                   const __nv_bfloat16* __restrict__ vp, int ld, int S, int group, int causal, float scale_log2,
                   __nv_bfloat16* __restrict__ out, int ld_out) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   constexpr int LDS = HDP + 8;          // smem row stride (elements): odd multiple of 16 B
   constexpr int CH = HD / 8;            // 16-byte chunks per global row
   constexpr int KSTEPS = HDP / 16;      // k-steps of QK^T
@@ -246,7 +249,7 @@ int launch_attn(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k
   }
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * 1.4426950408889634f;
   dim3 grid((Sq + ATT_BM - 1) / ATT_BM, n_heads, B);
-  flash_attn_kernel<HD, HDP><<<grid, ATT_THREADS, SMEM, s>>>(q, ld_q, Sq, k, v, ld, S, group, causal, scale_log2,
+  launch_kernel(flash_attn_kernel<HD, HDP>, dim3(grid), dim3(ATT_THREADS), SMEM, s, q, ld_q, Sq, k, v, ld, S, group, causal, scale_log2,
                                                             out, ld_out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

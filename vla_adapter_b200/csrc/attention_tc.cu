@@ -27,6 +27,7 @@
 // (32B-swizzled tiles) whose columns 72..79 are zero-filled by TMA: the tensor maps are per-head 4-D views
 // (d, head, row, sample) so that out-of-head columns count as out of bounds.
 #include "common.cuh"
+#include "launch.cuh"
 #include "ops.cuh"
 
 #include <algorithm>
@@ -345,6 +346,9 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // Everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp_idx < 4) {
   if (BN == 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
@@ -734,7 +738,7 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
     cudaMemsetAsync(p.trace, 0, 32004 * sizeof(unsigned int), s);
   }
   const int grid = std::min(p.n_items, L::CTAS_PER_SM * fa_num_sms());
-  fa_tcgen05_kernel<HD, BN><<<grid, FA_THREADS, L::TOTAL, s>>>(mQ, mK, mV, mQt, mKt, mVt, p);
+  launch_kernel(fa_tcgen05_kernel<HD, BN>, dim3(grid), dim3(FA_THREADS), L::TOTAL, s, mQ, mK, mV, mQt, mKt, mVt, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = cudaGetErrorString(e);

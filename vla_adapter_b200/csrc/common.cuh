@@ -77,6 +77,12 @@ VLA_DEVINL float2 gelu_erf2(float2 x) {
   return __ffma2_rn(h, pe, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Blocks until the grids this one depends on have completed and their writes are visible (no-op without PDL).
+VLA_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next kernel in the stream start being scheduled (it still waits in its own pdl_wait()).
+VLA_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 VLA_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

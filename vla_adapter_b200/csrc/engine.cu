@@ -8,6 +8,7 @@
 // (prismatic/models/action_heads.py:43-81) -> _unnormalize_actions (:786-805).
 #include "../../include/vla_b200.h"
 #include "gemm.cuh"
+#include "launch.cuh"
 #include "ops.cuh"
 
 #include <cmath>
@@ -319,6 +320,7 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, int B, int tower_i
 int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_t* aq_index, const float* proprio,
             int B, int L, float* out_norm, float* out_unnorm, bf16* out_last_ha, cudaStream_t s) {
   const int NP = e->NP, T = e->T, A = e->A, P = e->P;
+  vla::pdl_set(B <= 8);  // programmatic dependent launch pays off only when kernels are a few microseconds long
   const int Lext = L + N_AQ + 1;
   const int S = NP + Lext;
   const int M = B * S;

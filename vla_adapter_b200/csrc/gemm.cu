@@ -15,6 +15,7 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
 #include "common.cuh"
+#include "launch.cuh"
 #include "gemm.cuh"
 
 #include <atomic>
@@ -131,6 +132,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // Everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail.
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int num_kb = (p.K + BK - 1) / BK;
   const int total_tiles = p.tiles_m * p.tiles_n;
@@ -309,6 +313,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
 __global__ void __launch_bounds__(256)
 copy_view_kernel(const __nv_bfloat16* __restrict__ src, long long s_bs, int lds, __nv_bfloat16* __restrict__ dst,
                  long long d_bs, int ldd, int rows, int batches, int cols) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const int nvec = cols >> 3;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(batches) * rows * nvec;
@@ -478,7 +484,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   const bool accumulate = a.resid != nullptr;
   if (accumulate && !(a.resid == a.C && a.ldr == a.ldc && (a.batches == 1 || a.r_batch_stride == a.c_batch_stride))) {
     const long long total = static_cast<long long>(a.batches) * a.rows * (a.N >> 3);
-    copy_view_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+    launch_kernel(copy_view_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 
         a.resid, a.r_batch_stride, a.ldr, a.C, a.c_batch_stride, a.ldc, a.rows, a.batches, a.N);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
@@ -524,7 +530,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     cudaEventCreate(&rec.e1);
     cudaEventRecord(rec.e0, stream);
   }
-  gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(mA, mB, mC, p);
+  launch_kernel(gemm_bf16_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, stream, mA, mB, mC, p);
   if (prof) {
     cudaEventRecord(rec.e1, stream);
     std::lock_guard<std::mutex> lk(g_prof_mu);

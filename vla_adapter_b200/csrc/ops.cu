@@ -1,6 +1,7 @@
 // Bandwidth-bound kernels of the predict_action path: norms, RoPE, im2col, token assembly,
 // skinny linears.  All are vectorised (16-byte) and coalesced; reductions use warp shuffles.
 #include "common.cuh"
+#include "launch.cuh"
 #include "ops.cuh"
 
 #include <atomic>
@@ -29,6 +30,8 @@ __global__ void __launch_bounds__(256)
 norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long long x_bs, int dim, int ldx,
             const float* __restrict__ w, const float* __restrict__ b, float eps,
             __nv_bfloat16* __restrict__ y, long long y_bs, int ldy) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(rows) * batches;
@@ -115,6 +118,8 @@ __global__ void rope_table_kernel(float* cos_t, float* sin_t, int S, int half, f
 __global__ void __launch_bounds__(256)
 rope_apply_kernel(__nv_bfloat16* __restrict__ x, int ld, int off, int n_heads, long long rows, int S,
                   const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = rows * n_heads * 4;
   if (idx >= total) return;
@@ -155,6 +160,8 @@ rope_apply_kernel(__nv_bfloat16* __restrict__ x, int ld, int off, int n_heads, l
 __global__ void __launch_bounds__(256)
 im2col_kernel(const __nv_bfloat16* __restrict__ pix, int n_img, int tower, long long n_slabs,
               __nv_bfloat16* __restrict__ out) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   constexpr int KP = 592;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = n_slabs * 256 * 43;  // 42 (c,ky) segments + 1 zero-pad segment
@@ -183,6 +190,8 @@ im2col_kernel(const __nv_bfloat16* __restrict__ pix, int n_img, int tower, long 
 
 __global__ void prefix_tokens_kernel(__nv_bfloat16* __restrict__ x, int n_slabs, long long slab_stride,
                                      int dim, const __nv_bfloat16* __restrict__ prefix, int n_prefix) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const int nvec = dim >> 3;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n_slabs) * n_prefix * nvec;
@@ -201,6 +210,8 @@ assemble_kernel(__nv_bfloat16* __restrict__ x, int B, int S, int NP, int Lext, i
                 const int64_t* __restrict__ ext_ids, const int32_t* __restrict__ aq_index,
                 const __nv_bfloat16* __restrict__ embed, int vocab, const __nv_bfloat16* __restrict__ aq_table,
                 int n_aq, int* err_flag) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   // one block per (sample, text column j in [0, Lext))
   const int j = blockIdx.x % Lext;
   const int b = blockIdx.x / Lext;
@@ -231,6 +242,8 @@ __global__ void __launch_bounds__(256)
 skinny_linear_kernel(const void* __restrict__ x, int x_is_f32, int ldx, int M, int K,
                      const __nv_bfloat16* __restrict__ W, int ldw, int N, const float* __restrict__ bias,
                      int act, __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ out_f32) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= static_cast<long long>(M) * N) return;
@@ -271,6 +284,8 @@ skinny_linear_kernel(const void* __restrict__ x, int x_is_f32, int ldx, int M, i
 
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long src_bs, int ld, int r0,
                                    int rows, int batches, int dim, __nv_bfloat16* __restrict__ dst) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const int nvec = dim >> 3;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(batches) * rows * nvec;
@@ -285,6 +300,8 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long l
 
 __global__ void broadcast_row_kernel(const __nv_bfloat16* __restrict__ src, int dim, int rows,
                                      __nv_bfloat16* __restrict__ dst) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const int nvec = dim >> 3;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * nvec) return;
@@ -305,7 +322,7 @@ int layernorm_launch_3d(const __nv_bfloat16* x, int rows, int batches, long long
   }
   const long long total = static_cast<long long>(rows) * batches;
   const int blocks = static_cast<int>((total + 7) / 8);
-  norm_kernel<false><<<blocks, 256, 0, s>>>(x, rows, batches, x_bs, dim, ldx, w, b, eps, y, y_bs, ldy);
+  launch_kernel(norm_kernel<false>, dim3(blocks), dim3(256), 0, s, x, rows, batches, x_bs, dim, ldx, w, b, eps, y, y_bs, ldy);
   return check_launch(err);
 }
 
@@ -321,7 +338,7 @@ int rmsnorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const flo
     return -1;
   }
   const int blocks = (rows + 7) / 8;
-  norm_kernel<true><<<blocks, 256, 0, s>>>(x, rows, 1, 0, dim, ldx, w, nullptr, eps, y, 0, ldy);
+  launch_kernel(norm_kernel<true>, dim3(blocks), dim3(256), 0, s, x, rows, 1, 0, dim, ldx, w, nullptr, eps, y, 0, ldy);
   return check_launch(err);
 }
 
@@ -340,7 +357,7 @@ int rope_apply_launch(__nv_bfloat16* x, int ld, int off, int n_heads, int B, int
   }
   const long long rows = static_cast<long long>(B) * S;
   const long long total = rows * n_heads * 4;
-  rope_apply_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(x, ld, off, n_heads, rows, S, cos_t,
+  launch_kernel(rope_apply_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, x, ld, off, n_heads, rows, S, cos_t,
                                                                           sin_t);
   return check_launch(err);
 }
@@ -362,14 +379,14 @@ int im2col_launch(const __nv_bfloat16* pix, int B, int n_img, int tower, __nv_bf
                   const char** err) {
   const long long n_slabs = static_cast<long long>(B) * n_img;
   const long long total = n_slabs * 256 * 43;
-  im2col_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(pix, n_img, tower, n_slabs, out);
+  launch_kernel(im2col_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, pix, n_img, tower, n_slabs, out);
   return check_launch(err);
 }
 
 int prefix_tokens_launch(__nv_bfloat16* x, int n_slabs, long long slab_stride, int dim,
                          const __nv_bfloat16* prefix, int n_prefix, cudaStream_t s, const char** err) {
   const long long total = static_cast<long long>(n_slabs) * n_prefix * (dim >> 3);
-  prefix_tokens_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(x, n_slabs, slab_stride, dim,
+  launch_kernel(prefix_tokens_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, x, n_slabs, slab_stride, dim,
                                                                             prefix, n_prefix);
   return check_launch(err);
 }
@@ -377,7 +394,7 @@ int prefix_tokens_launch(__nv_bfloat16* x, int n_slabs, long long slab_stride, i
 int assemble_launch(__nv_bfloat16* x, int B, int S, int NP, int Lext, int dim, const int64_t* ext_ids,
                     const int32_t* aq_index, const __nv_bfloat16* embed, int vocab,
                     const __nv_bfloat16* aq_table, int n_aq, int* err_flag, cudaStream_t s, const char** err) {
-  assemble_kernel<<<B * Lext, 128, 0, s>>>(x, B, S, NP, Lext, dim, ext_ids, aq_index, embed, vocab, aq_table,
+  launch_kernel(assemble_kernel, dim3(B * Lext), dim3(128), 0, s, x, B, S, NP, Lext, dim, ext_ids, aq_index, embed, vocab, aq_table,
                                            n_aq, err_flag);
   return check_launch(err);
 }
@@ -386,7 +403,7 @@ int skinny_linear_launch(const void* x, int x_is_f32, int ldx, int M, int K, con
                          int N, const float* bias, int act, __nv_bfloat16* out, int ldo, float* out_f32,
                          cudaStream_t s, const char** err) {
   const long long warps = static_cast<long long>(M) * N;
-  skinny_linear_kernel<<<static_cast<int>((warps + 7) / 8), 256, 0, s>>>(x, x_is_f32, ldx, M, K, W, ldw, N,
+  launch_kernel(skinny_linear_kernel, dim3(static_cast<int>((warps + 7) / 8)), dim3(256), 0, s, x, x_is_f32, ldx, M, K, W, ldw, N,
                                                                         bias, act, out, ldo, out_f32);
   return check_launch(err);
 }
@@ -394,14 +411,14 @@ int skinny_linear_launch(const void* x, int x_is_f32, int ldx, int M, int K, con
 int broadcast_row_launch(const __nv_bfloat16* src, int dim, int rows, __nv_bfloat16* dst, cudaStream_t s,
                          const char** err) {
   const long long total = static_cast<long long>(rows) * (dim >> 3);
-  broadcast_row_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(src, dim, rows, dst);
+  launch_kernel(broadcast_row_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, src, dim, rows, dst);
   return check_launch(err);
 }
 
 int gather_rows_launch(const __nv_bfloat16* src, long long src_bs, int ld, int r0, int rows, int batches,
                        int dim, __nv_bfloat16* dst, cudaStream_t s, const char** err) {
   const long long total = static_cast<long long>(batches) * rows * (dim >> 3);
-  gather_rows_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(src, src_bs, ld, r0, rows, batches,
+  launch_kernel(gather_rows_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, src, src_bs, ld, r0, rows, batches,
                                                                           dim, dst);
   return check_launch(err);
 }

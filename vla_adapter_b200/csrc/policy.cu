@@ -9,6 +9,7 @@
 //     softmax([q k_self^T | q k_cond^T | g q k_vis^T] / sqrt(112)) [v_self; v_cond; v_vis]
 // is a single cross-attention call (attention.cu, hd = 112) on tensor cores.
 #include "common.cuh"
+#include "launch.cuh"
 #include "ops.cuh"
 
 namespace vla {
@@ -25,6 +26,8 @@ constexpr int PKV = 1792;   // K | V row
 __global__ void __launch_bounds__(256)
 policy_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ kv, int B, int T, int NP,
                    const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const int NK = T + 65 + NP;
   const int rows_per_b = T + NK;  // q rows then kv rows
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -84,6 +87,8 @@ head_out_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float* __re
                 const float* __restrict__ bias, int A, const float* __restrict__ hi,
                 const float* __restrict__ lo, const uint8_t* __restrict__ mask, float* __restrict__ out_norm,
                 float* __restrict__ out_unnorm) {
+  pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
+  pdl_launch_dependents();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -167,7 +172,7 @@ inline int finish(const char** err) {
 int policy_rope_launch(__nv_bfloat16* q, __nv_bfloat16* kv, int B, int T, int NP, const float* cos_t,
                        const float* sin_t, cudaStream_t s, const char** err) {
   const long long total = static_cast<long long>(B) * (2 * T + 65 + NP) * (PD / 8);
-  policy_rope_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(q, kv, B, T, NP, cos_t, sin_t);
+  launch_kernel(policy_rope_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, q, kv, B, T, NP, cos_t, sin_t);
   return finish(err);
 }
 
@@ -180,7 +185,7 @@ int policy_rope_table_launch(float* cos_t, float* sin_t, int max_pos, cudaStream
 int head_out_launch(const __nv_bfloat16* x, int rows, const float* ln_w, const float* ln_b,
                     const __nv_bfloat16* W, const float* bias, int A, const float* hi, const float* lo,
                     const uint8_t* mask, float* out_norm, float* out_unnorm, cudaStream_t s, const char** err) {
-  head_out_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, rows, ln_w, ln_b, W, bias, A, hi, lo, mask, out_norm,
+  launch_kernel(head_out_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, rows, ln_w, ln_b, W, bias, A, hi, lo, mask, out_norm,
                                                 out_unnorm);
   return finish(err);
 }
