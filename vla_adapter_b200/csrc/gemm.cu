@@ -82,6 +82,11 @@ VLA_DEVINL void store_box(const CUtensorMap* mapC, uint32_t buf_addr, int lane, 
   }
 }
 
+// CG = 1: one CTA per 128 x bn output tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x bn tile -
+// each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues 256 x bn x 16 MMAs that read both
+// CTAs' shared memory and write each CTA's 128 rows into its own TMEM; per FLOP that halves the B traffic through L2,
+// TMA and shared memory (the GEMM is power-capped on B200: less data movement = higher clocks).
+template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                          const __grid_constant__ CUtensorMap mapC, const GemmDev p) {
@@ -92,7 +97,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
   const uint32_t smem_base = raw_addr + pad;
 
   const int STAGES = p.stages;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * BK * 2;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn / CG) * BK * 2;  // this CTA's share of the B tile
   const uint32_t stage_bytes = A_BYTES + b_bytes;
   const uint32_t staging_base = smem_base + RING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + STAGING_BYTES);
@@ -119,17 +125,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);
+      mbar_init(tempty_bar(a), EPI_WARPS * CG);  // the leader's barrier collects the epilogue warps of both CTAs
     }
     mbar_fence_init();
     fence_proxy_async();
   }
   if (warp_idx == 1) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(smem_u32(tmem_slot), TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+      tmem_relinquish();
+    }
     tc_fence_before();
   }
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled across
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   // Everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail.
@@ -137,25 +149,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
   pdl_launch_dependents();
 
   const int num_kb = (p.K + BK - 1) / BK;
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int total_tiles = p.tiles_m * p.tiles_n;  // tiles of (BM * CG) rows x bn columns
+  const int tile0 = static_cast<int>(blockIdx.x) / CG, tile_step = static_cast<int>(gridDim.x) / CG;
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp waits, one lane issues)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int n_idx = tile % p.tiles_n;
       const int m_idx = tile / p.tiles_n;
       const int b = m_idx / p.mt_per_batch;
-      const int r0 = (m_idx - b * p.mt_per_batch) * BM;
-      const int n0 = n_idx * p.bn;
+      const int r0 = (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM;
+      const int n0 = n_idx * p.bn + static_cast<int>(crank) * (p.bn / CG);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          tma_load_3d(sa, &mapA, full_bar(stage), kb * BK, r0, b);
-          tma_load_3d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0, 0);
+          if (CG == 2) {
+            // both CTAs' loads are credited to the leader's barrier, which expects the bytes of the whole pair
+            if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes);
+            tma_load_3d_cg2(sa, &mapA, full_bar(stage), kb * BK, r0, b);
+            tma_load_3d_cg2(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0, 0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+            tma_load_3d(sa, &mapA, full_bar(stage), kb * BK, r0, b);
+            tma_load_3d(sa + A_BYTES, &mapB, full_bar(stage), kb * BK, n0, 0);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -166,12 +186,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     }
   } else if (warp_idx == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp waits, one lane issues)
-    const uint32_t idesc = make_idesc_bf16(BM, static_cast<uint32_t>(p.bn));
+    const uint32_t idesc = make_idesc_bf16(BM * CG, static_cast<uint32_t>(p.bn));
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    if (crank == 0)  // only the leader of a pair issues MMAs
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -185,9 +206,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_sw128_kmajor_desc(sa + k * 32);
             const uint64_t bdesc = make_sw128_kmajor_desc(sb + k * 32);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_bf16_cg2(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (CG == 2) umma_commit_cg2(empty_bar(stage), 3);
+          else umma_commit(empty_bar(stage));
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -195,7 +219,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
           phase ^= 1u;
         }
       }
-      if (elect_one()) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      if (elect_one()) {  // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 2) umma_commit_cg2(tfull_bar(acc), 3);
+        else umma_commit(tfull_bar(acc));
+      }
       __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -211,11 +238,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool swiglu = p.act == ACT_SWIGLU;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t tempty_leader0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : 0u;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int n_idx = tile % p.tiles_n;
       const int m_idx = tile / p.tiles_n;
       const int b = m_idx / p.mt_per_batch;
-      const int r0 = (m_idx - b * p.mt_per_batch) * BM + quarter * 32;
+      const int r0 = (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM + quarter * 32;
       const int n0 = n_idx * p.bn + half * wcols;
 
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -294,7 +322,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc);  // the leader's MMA warp owns the accumulators
+        else mbar_arrive(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -302,10 +333,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // neither CTA may leave while the pair's MMAs / remote arrivals can touch it
+  else __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -450,7 +483,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES) != cudaSuccess) {
       if (err) *err = "gemm: cudaFuncSetAttribute(max dynamic smem) failed";
       return -4;
@@ -458,9 +493,16 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     attr_set = true;
   }
 
-  const int mt_per_batch = (a.rows + BM - 1) / BM;
+  // CTA pairs (256-row tiles) whenever a row view is at least one pair tall; VLA_GEMM_CG=1/2 forces the choice.
+  static int cg_env = -1;
+  if (cg_env < 0) {
+    const char* e = getenv("VLA_GEMM_CG");
+    cg_env = e ? atoi(e) : 0;
+  }
+  const int cg = cg_env == 1 ? 1 : (cg_env == 2 ? 2 : (a.rows >= 2 * BM ? 2 : 1));
+  const int mt_per_batch = (a.rows + BM * cg - 1) / (BM * cg);
   const int tiles_m = mt_per_batch * a.batches;
-  const int sms = num_sms();
+  const int sms = num_sms() / cg;  // scheduling units: CTAs or CTA pairs
   // Tile-width heuristic: fewest (rounds over the SMs) x (tile width + fixed per-tile cost).
   int bn = a.force_bn;
   if (bn != 64 && bn != 128 && bn != 192 && bn != 256) {
@@ -498,7 +540,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.tiles_m = tiles_m;
   p.tiles_n = (a.N + bn - 1) / bn;
   p.bn = bn;
-  const uint32_t stage_bytes = A_BYTES + static_cast<uint32_t>(bn) * BK * 2;
+  const uint32_t stage_bytes = A_BYTES + static_cast<uint32_t>(bn / cg) * BK * 2;
   p.stages = static_cast<int>(RING_BYTES / stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.bias = a.bias;
@@ -513,7 +555,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
                                       : static_cast<uint64_t>(a.rows) * a.ldc;
   const uint64_t n_out = swiglu ? a.N / 2 : a.N;
   if (!make_map_3d(&mA, a.A, a.K, a.rows, a.batches, a.lda, a_bs, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B) ||
-      !make_map_3d(&mB, a.W, a.K, a.N, 1, a.ldw, static_cast<uint64_t>(a.N) * a.ldw, BK, bn,
+      !make_map_3d(&mB, a.W, a.K, a.N, 1, a.ldw, static_cast<uint64_t>(a.N) * a.ldw, BK, bn / cg,
                    CU_TENSOR_MAP_SWIZZLE_128B) ||
       !make_map_3d(&mC, a.C, n_out, a.rows, a.batches, a.ldc, c_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) {
     if (err) *err = "gemm: cuTensorMapEncodeTiled failed";
@@ -521,7 +563,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   }
 
   const int total = p.tiles_m * p.tiles_n;
-  const int grid = total < sms ? total : sms;
+  const int grid = (total < sms ? total : sms) * cg;
   ProfRec rec{};
   rec.rows = p.rows; rec.batches = p.batches; rec.N = p.N; rec.K = p.K; rec.bn = bn; rec.act = p.act;
   const bool prof = g_prof_on;
@@ -530,7 +572,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     cudaEventCreate(&rec.e1);
     cudaEventRecord(rec.e0, stream);
   }
-  launch_kernel(gemm_bf16_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, stream, mA, mB, mC, p);
+  if (cg == 2) launch_kernel_cluster(2, gemm_bf16_tcgen05_kernel<2>, dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, stream, mA, mB, mC, p);
+  else launch_kernel(gemm_bf16_tcgen05_kernel<1>, dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, stream, mA, mB, mC, p);
   if (prof) {
     cudaEventRecord(rec.e1, stream);
     std::lock_guard<std::mutex> lk(g_prof_mu);
