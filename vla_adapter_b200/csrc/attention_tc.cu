@@ -41,7 +41,7 @@ namespace vla {
 namespace {
 
 constexpr int FA_BM = 128;
-constexpr int FA_THREADS = 384;  // warpgroup 0: TMA + MMA warps (+2 idle), warpgroups 1/2: softmax of slot A/B
+constexpr int FA_THREADS = 640;  // warpgroup 0: TMA + MMA warps (+2 idle); warpgroups 1-2: softmax of slot A, 3-4: slot B
 constexpr uint32_t FA_TILE_BYTES = 128 * 128;  // Q tile: 128 rows x 64 bf16
 constexpr uint32_t FA_TAIL_BYTES = 128 * 32;   // Q tail: 128 rows x 16 bf16
 constexpr int FA_MAX_ITEMS = 24;               // work items per (sample, kv head)
@@ -172,55 +172,64 @@ VLA_DEVINL float ex2f(float x) {
   return y;
 }
 
-// Softmax of one 128-row x (NLIVE*32)-key score tile for this thread's query row: scores from TMEM, mask, running
-// max with lazy O rescale, exp2, row sum, P (bf16) back over the score columns.
+VLA_DEVINL void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Softmax of this thread's query row over ITS HALF of one 128-key score tile (NLIVE live chunks of 32 keys; the
+// partner warp of the same TMEM lane quarter owns the other 64 keys).  Scores from TMEM, mask, row max exchanged
+// with the partner through shared memory, running max with lazy O rescale, exp2, partial row sum, P (bf16) back
+// over the score columns.
 template <int HD, int NLIVE, bool MASKED>
-VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tS, uint32_t tO, int k0, int wrow0, int grow, int j, float sl2,
-                                float& m_ref, float& l, int tr_role, unsigned int& tr_cnt) {
-#ifdef VLA_FA_TRACE_BUILD
-  const bool tr = tr_role >= 0;
-#else
-  constexpr bool tr = false;
-#endif
-  uint32_t v[NLIVE][32];
+VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint32_t tO, int k0h, int grow, int j, int half,
+                                float sl2, float& m_ref, float& l, float* xch_mine, const float* xch_other, int bar_id,
+                                uint32_t turn_wait, uint32_t turn_parity, uint32_t turn_arrive) {
+  uint32_t v[NLIVE > 0 ? NLIVE : 1][32];
+  float mloc = -INFINITY;
+  if (NLIVE > 0) {
 #pragma unroll
-  for (int c = 0; c < NLIVE; ++c) tmem_ld_32x32b_x32(tS + c * 32, v[c]);
-  tmem_ld_wait();
-  if (tr) fa_trace(p, tr_role, tr_cnt, 700);
-  if (MASKED) {  // tile touches the causal diagonal or the end of the keys: straight-line select on every element
-    int last = p.Skv - 1;                        // last key this row may attend to ...
-    if (p.causal && grow < last) last = grow;
-    last -= k0;                                  // ... relative to this tile
+    for (int c = 0; c < NLIVE; ++c) tmem_ld_32x32b_x32(tSh + c * 32, v[c]);
+    tmem_ld_wait();
+    if (MASKED) {  // the half touches the causal diagonal or the end of the keys: straight-line select on every element
+      int last = p.Skv - 1;                        // last key this row may attend to ...
+      if (p.causal && grow < last) last = grow;
+      last -= k0h;                                 // ... relative to this half tile
 #pragma unroll
-    for (int c = 0; c < NLIVE; ++c)
+      for (int c = 0; c < NLIVE; ++c)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[c][i] = (c * 32 + i > last) ? 0xff800000u : v[c][i];  // -inf
-  }
-  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < NLIVE; ++c) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      mx0 = fmaxf(mx0, __uint_as_float(v[c][i]));
-      mx1 = fmaxf(mx1, __uint_as_float(v[c][i + 1]));
-      mx2 = fmaxf(mx2, __uint_as_float(v[c][i + 2]));
-      mx3 = fmaxf(mx3, __uint_as_float(v[c][i + 3]));
+        for (int i = 0; i < 32; ++i) v[c][i] = (c * 32 + i > last) ? 0xff800000u : v[c][i];  // -inf
     }
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NLIVE; ++c) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[c][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[c][i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(v[c][i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(v[c][i + 3]));
+      }
+    }
+    mloc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   }
-  const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+  // row max over the whole tile: one float per row each way, one 64-thread named barrier
+  *xch_mine = mloc;
+  named_bar_sync(bar_id, 64);
+  const float m_new = fmaxf(m_ref, fmaxf(mloc, *xch_other));
   if (j == 0) {
     m_ref = m_new;
   } else {
-    // Lazy rescale: the reference max only moves when it would otherwise let exp2 exceed 2^8.
+    // Lazy rescale: the reference max only moves when it would otherwise let exp2 exceed 2^8.  Both warps of the
+    // quarter see the same m_new / m_ref, so they take this branch together; each rescales its half of O's columns.
     const bool need = (m_new - m_ref) * sl2 > 8.0f;
     if (__any_sync(0xffffffffu, need)) {
       const float alpha = need ? ex2f((m_ref - m_new) * sl2) : 1.0f;
       if (need) m_ref = m_new;
       l *= alpha;
       // s_full(j) was committed after PV(j-1), so O is stable here and PV(j) has not been issued yet.
-      // (rare path: 8 columns at a time keeps its register footprint out of the hot loop's allocation)
+      constexpr int G = (HD + 7) / 8;
 #pragma unroll 1
-      for (int c = 0; c < (HD + 7) / 8; ++c) {
+      for (int c = half ? G / 2 : 0; c < (half ? G : G / 2); ++c) {
         uint32_t o[8];
         tmem_ld_32x32b_x8(tO + c * 8, o);
         tmem_ld_wait();
@@ -230,40 +239,44 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tS, uint32_t tO, int k0
       }
     }
   }
-  const float mb = m_ref * sl2;
-  float s0 = 0.f, s1 = 0.f;
-  if (tr) fa_trace(p, tr_role, tr_cnt, 701);
-  const float2 sl2v = make_float2(sl2, sl2), nmb = make_float2(-mb, -mb);
-  float2 sum2 = make_float2(0.f, 0.f);
+  // The exponentials of the two slots take turns: while one slot owns the MUFU, the other's P -> PV -> next QK ->
+  // TMEM load -> row max chain runs on the tensor pipe, instead of both slots doing each phase in lockstep.
+  if (turn_wait) mbar_wait(turn_wait, turn_parity);
+  if (NLIVE > 0) {
+    const float mb = m_ref * sl2;
+    const float2 sl2v = make_float2(sl2, sl2), nmb = make_float2(-mb, -mb);
+    float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < NLIVE; ++c) {
-    // phase 1: all 32 exponentials of the chunk in flight (packed FFMA2 for the scale/shift)
+    for (int c = 0; c < NLIVE; ++c) {
+      // phase 1: all 32 exponentials of the chunk in flight (packed FFMA2 for the scale/shift)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2v, nmb);
-      v[c][2 * i] = __float_as_uint(ex2f(t.x));
-      v[c][2 * i + 1] = __float_as_uint(ex2f(t.y));
+      for (int i = 0; i < 16; ++i) {
+        const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2v, nmb);
+        v[c][2 * i] = __float_as_uint(ex2f(t.x));
+        v[c][2 * i + 1] = __float_as_uint(ex2f(t.y));
+      }
+      // phase 2: row sum (packed FADD2) and bf16 packing
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 e = make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]));
+        sum2 = __fadd2_rn(sum2, e);
+        pk[i] = pack_bf16(e.x, e.y);
+      }
+      tmem_st_32x32b_x16(tPh + c * 16, pk);
     }
-    // phase 2: row sum (packed FADD2) and bf16 packing
-    uint32_t pk[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float2 e = make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]));
-      sum2 = __fadd2_rn(sum2, e);
-      pk[i] = pack_bf16(e.x, e.y);
-    }
-    tmem_st_32x32b_x16(tS + c * 16, pk);
+    l += sum2.x + sum2.y;
   }
-  s0 = sum2.x;
-  s1 = sum2.y;
-  if (tr) fa_trace(p, tr_role, tr_cnt, 703);
-  l += s0 + s1;
+  if (turn_arrive) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(turn_arrive);
+  }
 }
 
 template <int HD, int BN>
 struct FaSmem {
   static constexpr bool TAIL = HD > 64;
-  static constexpr int CTAS_PER_SM = BN == 64 ? 2 : 1;
+  static constexpr int CTAS_PER_SM = 1;
   static constexpr int STAGES = 3;
   static constexpr int QBUFS = 4;  // 2 slots x 2 buffers: the next item's Q tiles land while this item computes
   static constexpr uint32_t KV_TILE = BN * 128;  // BN keys x 64 bf16
@@ -278,11 +291,12 @@ struct FaSmem {
   static constexpr uint32_t OFF_KT = OFF_QT + QBUFS * FA_TAIL_BYTES;
   static constexpr uint32_t OFF_VT = OFF_KT + STAGES * KV_TAIL;
   static constexpr uint32_t OFF_BAR = TAIL ? OFF_VT + STAGES * KV_TAIL : OFF_QT;
-  static constexpr uint32_t TOTAL = OFF_BAR + 256;  // the dynamic array is declared __align__(1024): no slack needed
+  static constexpr uint32_t OFF_XCH = OFF_BAR + 256;  // row-max / row-sum exchange: [slot][parity][half][128] floats
+  static constexpr uint32_t TOTAL = OFF_XCH + 2 * 2 * 2 * 128 * 4;  // the dynamic array is __align__(1024): no slack
   // TMEM columns: S_A [0,BN), S_B [BN,2BN) (P aliases the first half of S), then O_A, O_B
   static constexpr uint32_t O_OFF = 2 * BN;
   static constexpr uint32_t O_STRIDE = TAIL ? 128 : 64;
-  static constexpr uint32_t TMEM_COLS = BN == 64 ? 256 : 512;
+  static constexpr uint32_t TMEM_COLS = 512;
   static_assert(!(TAIL && BN == 64), "head dim 72 needs 2*64 + 2*80 TMEM columns: use BN = 128");
 };
 
@@ -308,6 +322,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   auto p_ready = [&](int x) { return bar_base + 8u * (10 + x); };
   auto o_full = [&](int x) { return bar_base + 8u * (12 + x); };
   auto o_empty = [&](int x) { return bar_base + 8u * (14 + x); };
+  auto turn = [&](int x) { return bar_base + 8u * (16 + x); };        // exp-phase turn taking between the slots
   auto kv_full = [&](int s) { return bar_base + 8u * (18 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (18 + NS + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_BAR + 8 * (18 + 2 * NS));
@@ -326,10 +341,11 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       mbar_init(q_empty(qb), 1);
     }
     for (int x = 0; x < 2; ++x) {
+      mbar_init(turn(x), 8);
       mbar_init(s_full(x), 1);
-      mbar_init(p_ready(x), 128);
+      mbar_init(p_ready(x), 256);
       mbar_init(o_full(x), 1);
-      mbar_init(o_empty(x), 128);
+      mbar_init(o_empty(x), 256);
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(kv_full(s), 1);
@@ -351,8 +367,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   pdl_launch_dependents();
 
   if (warp_idx < 4) {
-  if (BN == 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");  // 128*32 + 512*112 == 640*96 (launch allocation)
   if (warp_idx == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp waits, one lane issues)
     uint32_t kv_cnt = 0, q_cnt[2] = {0, 0};
@@ -493,16 +508,23 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     }
   }
   } else {
-    if (BN == 64) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 128*32 + 256*104 == 384*80 (launch allocation)
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    // ------------------------------------------------------------ softmax + epilogue: one thread per query row
-    const int x = (warp_idx - 4) >> 2;   // slot
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ------------------------------------------------------------ softmax + epilogue
+    // 8 warps per slot: the two warps of one TMEM lane quarter own the same 32 query rows (one thread per row) and
+    // split the tile's 128 keys (and later O's columns) in halves - four softmax warps per SM sub-partition keep the
+    // MUFU busy where one warp per sub-partition reaches only ~57 % of its rate (scripts/ubench/expmix.cu).
+    static_assert(BN == 128, "the split-column softmax assumes 128-key tiles");
+    const int x = (warp_idx - 4) >> 3;   // slot
     const int quarter = warp_idx & 3;    // TMEM lane quarter this warp may touch
+    const int half = ((warp_idx - 4) >> 2) & 1;  // which 64 keys of a tile / which half of O's columns
     const int row = quarter * 32 + lane;
     const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(BN) * x;
     const uint32_t tO = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + L::O_OFF + L::O_STRIDE * x;
+    const uint32_t tSh = tS + 64u * half, tPh = tS + 32u * half;
+    float* xch = reinterpret_cast<float*>(smem + L::OFF_XCH) + x * 512;  // [parity][half][128]
+    const int bar_id = 1 + x * 4 + quarter;
     const float sl2 = p.scale_log2;
-    uint32_t s_cnt = 0, o_cnt = 0;
+    uint32_t s_cnt = 0, o_cnt = 0, x_cnt = 0, t_cnt = 0;
     unsigned int tr_cnt = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const FaItem it = fa_decode(p, item);
@@ -511,8 +533,12 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       const int q0 = it.qb[x] * FA_BM;
       const int grow = q0 + row;
       const int wrow0 = q0 + quarter * 32;            // first query row of this warp
-      const bool warp_active = wrow0 < p.Sq;          // warps whose rows are all padding only keep the barriers moving
+      const bool warp_active = wrow0 < p.Sq && !(p.debug & 1);  // all-padding warps only keep the barriers moving
       float m_ref = -INFINITY, l = 0.f;
+      // turn taking needs both slots busy with all their warps (padding-only warps would break the arrival counts)
+      const bool pp = !(p.debug & 8) && it.n[0] && it.n[1] && it.qb[0] * FA_BM + FA_BM <= p.Sq &&
+                      it.qb[1] * FA_BM + FA_BM <= p.Sq && !(p.debug & 1);
+      const int m_pp = it.n[0] < it.n[1] ? it.n[0] : it.n[1];
       for (int j = 0; j < n_it; ++j) {
         const int k0 = j * BN;
         int nvalid = p.Skv - k0;
@@ -521,78 +547,89 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         mbar_wait(s_full(x), s_cnt & 1u);
         ++s_cnt;
         tc_fence_after();
-        if (quarter == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 400 + x * 10 + j);
-#ifdef VLA_FA_TRACE_BUILD
-        const int tr_role = (p.trace && blockIdx.x == 0 && quarter == 0 && lane == 0) ? 2 + x : -1;
-#else
-        constexpr int tr_role = -1;
-#endif
-        if (warp_active && !(p.debug & 1)) {
+        if (quarter == 0 && half == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 400 + x * 10 + j);
+        if (warp_active) {
           // causal: chunks entirely above the diagonal for every row of this warp carry no probability mass
           int nlive = nch;
           if (p.causal) {
             const int lim = (wrow0 + 31 - k0) / 32 + 1;  // chunks with a key <= the warp's last row
             nlive = lim < nch ? (lim < 0 ? 0 : lim) : nch;
           }
-          // warp-uniform: does any live chunk touch the causal diagonal or the end of the keys?
-          const bool masked = (k0 + nlive * 32 > p.Skv) || (p.causal && k0 + nlive * 32 - 1 > wrow0);
-          if constexpr (BN == 64) {
-            if (nlive == 1) (masked ? fa_softmax_tile<HD, 1, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
-                    : fa_softmax_tile<HD, 1, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt));
-            else (masked ? fa_softmax_tile<HD, 2, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
-                    : fa_softmax_tile<HD, 2, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt));
+          // this warp's half: chunks [2*half, 2*half + 2) of the tile
+          int my_live = nlive - 2 * half, my_all = nch - 2 * half;
+          my_live = my_live < 0 ? 0 : (my_live > 2 ? 2 : my_live);
+          my_all = my_all < 0 ? 0 : (my_all > 2 ? 2 : my_all);
+          const int k0h = k0 + 64 * half;
+          // warp-uniform: does a live chunk of this half touch the causal diagonal or the end of the keys?
+          const bool masked = (k0h + my_live * 32 > p.Skv) || (p.causal && k0h + my_live * 32 - 1 > wrow0);
+          float* xm = xch + (x_cnt & 1u) * 256 + half * 128 + row;
+          const float* xo = xch + (x_cnt & 1u) * 256 + (half ^ 1) * 128 + row;
+          ++x_cnt;
+          // exp-phase turn taking while both slots are busy: A(j) -> B(j) -> A(j+1) ...
+          const bool do_wait = pp && (x == 0 ? (j > 0 && j < m_pp) : (j < m_pp));
+          const bool do_arrive = pp && (x == 0 ? (j < m_pp) : (j + 1 < m_pp));
+          const uint32_t t_wait = do_wait ? turn(x) : 0u, t_par = t_cnt & 1u, t_arr = do_arrive ? turn(x ^ 1) : 0u;
+          if (do_wait) ++t_cnt;
+          if (my_live == 2) {
+            if (masked) fa_softmax_tile<HD, 2, true>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
+            else fa_softmax_tile<HD, 2, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
+          } else if (my_live == 1) {
+            if (masked) fa_softmax_tile<HD, 1, true>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
+            else fa_softmax_tile<HD, 1, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
           } else {
-            switch (nlive) {
-              case 1: (masked ? fa_softmax_tile<HD, 1, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
-                    : fa_softmax_tile<HD, 1, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)); break;
-              case 2: (masked ? fa_softmax_tile<HD, 2, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
-                    : fa_softmax_tile<HD, 2, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)); break;
-              case 3: (masked ? fa_softmax_tile<HD, 3, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
-                    : fa_softmax_tile<HD, 3, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)); break;
-              default: (masked ? fa_softmax_tile<HD, 4, true>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)
-                    : fa_softmax_tile<HD, 4, false>(p, tS, tO, k0, wrow0, grow, j, sl2, m_ref, l, tr_role, tr_cnt)); break;
-            }
+            fa_softmax_tile<HD, 0, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
           }
-          if (nlive < nch) {  // causal chunks above the diagonal: P = 0
+          if (my_live < my_all) {  // causal chunks above the diagonal: P = 0
             uint32_t z[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) z[i] = 0u;
-            for (int c = nlive; c < nch; ++c) tmem_st_32x32b_x16(tS + c * 16, z);
+            for (int c = my_live; c < my_all; ++c) tmem_st_32x32b_x16(tPh + c * 16, z);
           }
           tmem_st_wait();
         }
         tc_fence_before();
-        if (quarter == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 500 + x * 10 + j);
+        if (quarter == 0 && half == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 500 + x * 10 + j);
         mbar_arrive(p_ready(x));
       }
-      // ---- epilogue: O / l -> bf16 -> global (each thread owns one output row of this head)
+      // ---- epilogue: O / l -> bf16 -> global; each warp takes its half of the head's columns of its 32 rows
+      float l_tot = l;
+      if (warp_active) {  // total row sum = this warp's keys + the partner's
+        float* xm = xch + (x_cnt & 1u) * 256 + half * 128 + row;
+        const float* xo = xch + (x_cnt & 1u) * 256 + (half ^ 1) * 128 + row;
+        ++x_cnt;
+        *xm = l;
+        named_bar_sync(bar_id, 64);
+        l_tot = l + *xo;
+      }
       mbar_wait(o_full(x), o_cnt & 1u);
       ++o_cnt;
       tc_fence_after();
-      if (quarter == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 600 + x);
-      uint32_t o[(HD + 31) / 32][32];
+      if (quarter == 0 && half == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 600 + x);
+      constexpr int G = (HD + 7) / 8;                  // 8-column groups of the head
+      constexpr int G0 = G / 2;                        // half 0: groups [0, G0), half 1: [G0, G)
+      constexpr int GMAX = G - G0;
+      uint32_t o[GMAX][8];
+      const int g_lo = half ? G0 : 0, g_n = half ? G - G0 : G0;
       if (warp_active) {
 #pragma unroll
-        for (int c = 0; c < (HD + 31) / 32; ++c) tmem_ld_32x32b_x32(tO + c * 32, o[c]);
+        for (int c = 0; c < GMAX; ++c)
+          if (c < g_n) tmem_ld_32x32b_x8(tO + (g_lo + c) * 8, o[c]);
         tmem_ld_wait();
       }
       tc_fence_before();
       mbar_arrive(o_empty(x));  // O_x may be overwritten by the next item's first PV
       if (warp_active && grow < p.Sq) {
-        const float inv = 1.0f / l;
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.Sq + grow) * p.ld_out + it.h[x] * HD;
+        const float inv = 1.0f / l_tot;
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.Sq + grow) * p.ld_out + it.h[x] * HD + g_lo * 8;
 #pragma unroll
-        for (int c = 0; c < (HD + 31) / 32; ++c) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (c * 32 + q * 8 < HD) {
-              uint4 w;
-              w.x = pack_bf16(__uint_as_float(o[c][8 * q]) * inv, __uint_as_float(o[c][8 * q + 1]) * inv);
-              w.y = pack_bf16(__uint_as_float(o[c][8 * q + 2]) * inv, __uint_as_float(o[c][8 * q + 3]) * inv);
-              w.z = pack_bf16(__uint_as_float(o[c][8 * q + 4]) * inv, __uint_as_float(o[c][8 * q + 5]) * inv);
-              w.w = pack_bf16(__uint_as_float(o[c][8 * q + 6]) * inv, __uint_as_float(o[c][8 * q + 7]) * inv);
-              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = w;
-            }
+        for (int c = 0; c < GMAX; ++c) {
+          if (c < g_n) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(o[c][0]) * inv, __uint_as_float(o[c][1]) * inv);
+            w.y = pack_bf16(__uint_as_float(o[c][2]) * inv, __uint_as_float(o[c][3]) * inv);
+            w.z = pack_bf16(__uint_as_float(o[c][4]) * inv, __uint_as_float(o[c][5]) * inv);
+            w.w = pack_bf16(__uint_as_float(o[c][6]) * inv, __uint_as_float(o[c][7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 8) = w;
           }
         }
       }

@@ -26,7 +26,7 @@ constexpr int MAX_VEC_PER_LANE = 5;  // dim <= 5*32*8 = 1280
 // ------------------------------------------------------------------ LayerNorm / RMSNorm
 // One warp per row.  The row is read once into registers (16-byte loads), statistics in fp32.
 template <bool RMS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long long x_bs, int dim, int ldx,
             const float* __restrict__ w, const float* __restrict__ b, float eps,
             __nv_bfloat16* __restrict__ y, long long y_bs, int ldy) {
@@ -42,18 +42,25 @@ norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long lon
   __nv_bfloat16* yr = y + bi * y_bs + static_cast<long long>(r) * ldy;
   const int nvec = dim >> 3;
 
-  float v[MAX_VEC_PER_LANE][8];
+  // The row stays packed (bf16) in registers - 4 registers per 16-byte vector instead of 8 floats - so that the
+  // kernel fits 2048 threads per SM and keeps enough loads in flight to approach the HBM roofline.
+  uint4 u[MAX_VEC_PER_LANE];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
     const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
-      const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
-      v[i][0] = a0.x; v[i][1] = a0.y; v[i][2] = a1.x; v[i][3] = a1.y;
-      v[i][4] = a2.x; v[i][5] = a2.y; v[i][6] = a3.x; v[i][7] = a3.y;
+    if (vi < nvec) u[i] = *reinterpret_cast<const uint4*>(xr + vi * 8);
+  }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum += RMS ? v[i][j] * v[i][j] : v[i][j];
+  for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint32_t w4[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16(w4[j]);
+        sum += RMS ? a.x * a.x + a.y * a.y : a.x + a.y;
+      }
     }
   }
   sum = warp_sum(sum);
@@ -67,10 +74,12 @@ norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long lon
     for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
+        const uint32_t w4[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[i][j] - mean;
-          var += d * d;
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = unpack_bf16(w4[j]);
+          const float d0 = a.x - mean, d1 = a.y - mean;
+          var += d0 * d0 + d1 * d1;
         }
       }
     }
@@ -84,17 +93,25 @@ norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long lon
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + vi * 8));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + vi * 8 + 4));
       const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const uint32_t w4[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16(w4[j]);
+        v[2 * j] = a.x;
+        v[2 * j + 1] = a.y;
+      }
       float o[8];
       if (RMS) {
         // HF: weight * (x_fp32 * rsqrt(var + eps)).to(bf16)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = ww[j] * bf16_round(v[i][j] * rstd);
+        for (int j = 0; j < 8; ++j) o[j] = ww[j] * bf16_round(v[j] * rstd);
       } else {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + vi * 8));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + vi * 8 + 4));
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * ww[j] + bb[j];
+        for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd * ww[j] + bb[j];
       }
       *reinterpret_cast<uint4*>(yr + vi * 8) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
                                                           pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
