@@ -109,10 +109,21 @@ struct vla_engine {
 
   // workspace
   int maxB = 0, maxL = 0, maxS = 0;
-  bf16 *w_col, *w_x, *w_xn, *w_qkv, *w_attn, *w_h, *w_patches, *w_ph1, *w_ph2;
+  struct TowerWs {
+    bf16 *col, *x, *xn, *qkv, *attn, *h;
+  };
+  TowerWs tw[2];  // one workspace per vision tower: at small batch the towers run concurrently on two streams
+  bf16 *w_patches, *w_ph1, *w_ph2;
   std::vector<bf16*> hid;  // 25 LLM states
   bf16 *l_tmp, *l_xn, *l_qkv, *l_attn, *l_act;
   bf16 *h_p1, *h_p, *h_kv, *h_q, *h_ao, *h_y, *h_yn;
+  // small-batch mode (B <= small_B): every policy block has its own K|V buffer so that the K|V projections of the
+  // LLM states run on a side stream as soon as each LLM layer finishes, off the policy's critical path
+  int small_B = 0;
+  std::vector<bf16*> h_kv_blk;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_layer, ev_kv;
   std::vector<bf16*> head_x;  // 25 policy states
   int* err_flag = nullptr;
   // pinned/dev staging for vla_predict_host
@@ -268,13 +279,14 @@ void build_tower(vla_engine* e, Tower& t, const std::string& pfx, bool is_dino, 
 int run_tower(vla_engine* e, const Tower& t, const bf16* pix, int B, int tower_idx, cudaStream_t s) {
   const int n = e->cfg.n_images, slabs = B * n, D = t.D, F = t.F;
   const int M = slabs * t.tokens;
-  bf16* x = e->w_x;
-  CK(vla::im2col_launch(pix, B, n, tower_idx, e->w_col, s, &_err));
+  const vla_engine::TowerWs& ws = e->tw[tower_idx];
+  bf16* x = ws.x;
+  CK(vla::im2col_launch(pix, B, n, tower_idx, ws.col, s, &_err));
   if (t.prefix) CK(vla::prefix_tokens_launch(x, slabs, static_cast<long long>(t.tokens) * D, D, t.prefix_rows, t.prefix, s, &_err));
   {
     // patch embed (+bias +pos_embed) written behind the prefix rows of every image slab
     vla::GemmArgs g;
-    g.A = e->w_col; g.a_batch_stride = 256LL * KP; g.lda = KP; g.rows = 256; g.batches = slabs;
+    g.A = ws.col; g.a_batch_stride = 256LL * KP; g.lda = KP; g.rows = 256; g.batches = slabs;
     g.W = t.wpatch; g.ldw = KP; g.N = D; g.K = KP;
     g.C = x + static_cast<long long>(t.prefix) * D; g.c_batch_stride = static_cast<long long>(t.tokens) * D; g.ldc = D;
     g.bias = t.bpatch; g.resid = t.pos; g.r_batch_stride = 0; g.ldr = D;
@@ -284,36 +296,70 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, int B, int tower_i
   for (int i = 0; i < nblk; ++i) {
     const VitBlock& k = t.blocks[i];
     const bool last = (i == nblk - 1);
-    CK(vla::layernorm_launch(x, M, D, D, k.ln1w, k.ln1b, VIT_EPS, e->w_xn, D, s, &_err));
+    CK(vla::layernorm_launch(x, M, D, D, k.ln1w, k.ln1b, VIT_EPS, ws.xn, D, s, &_err));
     vla::GemmArgs g;
-    g.A = e->w_xn; g.lda = D; g.rows = M; g.W = k.wqkv; g.ldw = D; g.N = 3 * D; g.K = D;
-    g.C = e->w_qkv; g.ldc = 3 * D; g.bias = k.bqkv;
+    g.A = ws.xn; g.lda = D; g.rows = M; g.W = k.wqkv; g.ldw = D; g.N = 3 * D; g.K = D;
+    g.C = ws.qkv; g.ldc = 3 * D; g.bias = k.bqkv;
     CK(vla::gemm_launch(g, s, &_err));
-    CK(vla::attention_launch(e->w_qkv, 3 * D, 0, D, 2 * D, slabs, t.tokens, t.heads, 1, t.hd, 0, e->w_attn, D, s, &_err));
+    CK(vla::attention_launch(ws.qkv, 3 * D, 0, D, 2 * D, slabs, t.tokens, t.heads, 1, t.hd, 0, ws.attn, D, s, &_err));
     g = vla::GemmArgs();
-    g.A = e->w_attn; g.lda = D; g.rows = M; g.W = k.wproj; g.ldw = D; g.N = D; g.K = D;
+    g.A = ws.attn; g.lda = D; g.rows = M; g.W = k.wproj; g.ldw = D; g.N = D; g.K = D;
     g.C = x; g.ldc = D; g.bias = k.bproj; g.colscale = k.ls1; g.resid = x; g.ldr = D;
     CK(vla::gemm_launch(g, s, &_err));
-    CK(vla::layernorm_launch(x, M, D, D, k.ln2w, k.ln2b, VIT_EPS, e->w_xn, D, s, &_err));
+    CK(vla::layernorm_launch(x, M, D, D, k.ln2w, k.ln2b, VIT_EPS, ws.xn, D, s, &_err));
     g = vla::GemmArgs();
-    g.A = e->w_xn; g.lda = D; g.rows = M; g.W = k.wfc1; g.ldw = D; g.N = F; g.K = D;
-    g.C = e->w_h; g.ldc = F; g.bias = k.bfc1; g.act = vla::ACT_GELU;
+    g.A = ws.xn; g.lda = D; g.rows = M; g.W = k.wfc1; g.ldw = D; g.N = F; g.K = D;
+    g.C = ws.h; g.ldc = F; g.bias = k.bfc1; g.act = vla::ACT_GELU;
     CK(vla::gemm_launch(g, s, &_err));
     g = vla::GemmArgs();
     g.W = k.wfc2; g.ldw = F; g.N = D; g.K = F; g.bias = k.bfc2; g.colscale = k.ls2;
     if (!last) {
-      g.A = e->w_h; g.lda = F; g.rows = M;
+      g.A = ws.h; g.lda = F; g.rows = M;
       g.C = x; g.ldc = D; g.resid = x; g.ldr = D;
     } else {
       // Output block: only the patch rows (prefix stripped, film_vit_wrapper.py:162) go to the
       // feature-concatenated buffer (modeling_prismatic.py:233, 237).
-      g.A = e->w_h + static_cast<long long>(t.prefix) * F; g.a_batch_stride = static_cast<long long>(t.tokens) * F;
+      g.A = ws.h + static_cast<long long>(t.prefix) * F; g.a_batch_stride = static_cast<long long>(t.tokens) * F;
       g.lda = F; g.rows = 256; g.batches = slabs;
       g.resid = x + static_cast<long long>(t.prefix) * D; g.r_batch_stride = static_cast<long long>(t.tokens) * D; g.ldr = D;
       g.C = e->w_patches + (tower_idx == 0 ? 0 : D_DINO); g.c_batch_stride = 256LL * D_VIS; g.ldc = D_VIS;
     }
     CK(vla::gemm_launch(g, s, &_err));
   }
+  return 0;
+}
+
+// K|V projections of one policy block that depend only on LLM hidden state i+1: the 64 ActionQuery rows -> kv rows
+// [T, T+64) and the NP raw rows -> kv rows [T+65, NK), K columns of the latter scaled by tanh(gating_factor)
+// (AH:269 / AH:391).
+int policy_kv_gemms(vla_engine* e, int i, const bf16* hs, int B, int L, bf16* kvb, cudaStream_t s) {
+  const int NP = e->NP, T = e->T;
+  const int S = NP + L + N_AQ + 1;
+  const int ha_row0 = NP + L - 1;  // MP:855 with NUM_PROMPT_TOKENS = L-1 (MP:927)
+  const long long kv_bs = static_cast<long long>(T + N_AQ + 1 + NP) * PKV;
+  const HeadBlock& w = e->head[i];
+  vla::GemmArgs g;
+  g.A = hs + static_cast<long long>(ha_row0) * D_LLM; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM;
+  g.rows = N_AQ; g.batches = B; g.W = w.wkv_cond; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
+  g.C = kvb + static_cast<long long>(T) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_cond;
+  CK(vla::gemm_launch(g, s, &_err));
+  g = vla::GemmArgs();
+  g.A = hs; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM; g.rows = NP; g.batches = B;
+  g.W = w.wkv_vis; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
+  g.C = kvb + static_cast<long long>(T + N_AQ + 1) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV;
+  g.bias = w.bkv_vis; g.colscale = w.gatevec;
+  CK(vla::gemm_launch(g, s, &_err));
+  return 0;
+}
+
+// Small-batch mode: the same projections on the side stream, ordered after LLM layer i by an event on the main stream
+// and announced to the policy loop by ev_kv[i].
+int policy_kv_from_llm(vla_engine* e, int i, const bf16* hs, int B, int L, cudaStream_t s, cudaStream_t s2) {
+  if (cudaEventRecord(e->ev_layer[i], s) != cudaSuccess || cudaStreamWaitEvent(s2, e->ev_layer[i], 0) != cudaSuccess)
+    return e->fail(VLA_ERR_CUDA, "policy K|V fork failed");
+  const int rc = policy_kv_gemms(e, i, hs, B, L, e->h_kv_blk[i], s2);
+  if (rc) return rc;
+  if (cudaEventRecord(e->ev_kv[i], s2) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V event failed");
   return 0;
 }
 
@@ -326,11 +372,24 @@ int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_
   const int M = B * S;
   const int NL = e->cfg.llm_layers;
 
+  // Small batches leave most SMs idle inside every kernel: independent work goes to a side stream (the fork / join
+  // are events, so inside a captured CUDA graph they become parallel branches).
+  const bool small = e->small_B > 0 && B <= e->small_B;
+  cudaStream_t s2 = small ? e->side : s;
+
   // ---------------- vision towers + projector (MP:196-237, 261-273)
-  int rc = run_tower(e, e->dino, pix, B, 0, s);
+  if (small) {
+    if (cudaEventRecord(e->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(s2, e->ev_fork, 0) != cudaSuccess)
+      return e->fail(VLA_ERR_CUDA, "side stream fork failed");
+  }
+  int rc = run_tower(e, e->dino, pix, B, 0, s2);  // the shorter tower rides on the side stream
   if (rc) return rc;
   rc = run_tower(e, e->sig, pix, B, 1, s);
   if (rc) return rc;
+  if (small) {
+    if (cudaEventRecord(e->ev_join, s2) != cudaSuccess || cudaStreamWaitEvent(s, e->ev_join, 0) != cudaSuccess)
+      return e->fail(VLA_ERR_CUDA, "side stream join failed");
+  }
   {
     vla::GemmArgs g;
     g.A = e->w_patches; g.lda = D_VIS; g.rows = B * NP; g.W = e->pj_w1; g.ldw = D_VIS; g.N = D_PROJ1; g.K = D_VIS;
@@ -376,9 +435,17 @@ int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_
     g.A = e->l_act; g.lda = I_LLM; g.rows = M; g.W = w.wdown; g.ldw = I_LLM; g.N = D_LLM; g.K = I_LLM;
     g.C = xout; g.ldc = D_LLM; g.resid = xout; g.ldr = D_LLM;
     CK(vla::gemm_launch(g, s, &_err));
+    if (small && l + 1 < NL) {  // hid[l+1] is final: its policy K|V projections start now, beside the next LLM layer
+      rc = policy_kv_from_llm(e, l, e->hid[l + 1], B, L, s, s2);
+      if (rc) return rc;
+    }
   }
   // hidden_states[-1] is the post-final-norm state (HF output_hidden_states semantics)
   CK(vla::rmsnorm_launch(e->l_tmp, M, D_LLM, D_LLM, e->llm_norm, LLM_EPS, e->hid[NL], D_LLM, s, &_err));
+  if (small) {
+    rc = policy_kv_from_llm(e, NL - 1, e->hid[NL], B, L, s, s2);
+    if (rc) return rc;
+  }
 
   // ---------------- Bridge-Attention policy (AH:43-81, 111-121, 218-283 / 337-410)
   CK(vla::skinny_linear_launch(proprio, 1, P, B, P, e->pp_w1, P, D_LLM, e->pp_b1, 1, e->h_p1, D_LLM, nullptr, s, &_err));
@@ -392,24 +459,20 @@ int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_
   for (int i = 0; i < NB; ++i) {
     const HeadBlock& w = e->head[i];
     const bf16* hs = e->hid[i + 1];  // AH:118: block i reads hidden state i+1
-    // K|V of the 64 ActionQuery rows -> kv rows [T, T+64)
+    bf16* kvb = small ? e->h_kv_blk[i] : e->h_kv;
     vla::GemmArgs g;
-    g.A = hs + static_cast<long long>(ha_row0) * D_LLM; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM;
-    g.rows = N_AQ; g.batches = B; g.W = w.wkv_cond; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
-    g.C = e->h_kv + static_cast<long long>(T) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_cond;
-    CK(vla::gemm_launch(g, s, &_err));
+    if (small) {
+      // the LLM-state K|V rows of this block were projected on the side stream (policy_kv_from_llm)
+      if (cudaStreamWaitEvent(s, e->ev_kv[i], 0) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V join failed");
+    } else {
+      rc = policy_kv_gemms(e, i, hs, B, L, kvb, s);
+      if (rc) return rc;
+    }
     // K|V of the proprio row -> kv row T+64
     g = vla::GemmArgs();
     g.A = e->h_p; g.a_batch_stride = D_LLM; g.lda = D_LLM; g.rows = 1; g.batches = B;
     g.W = w.wkv_cond; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
-    g.C = e->h_kv + static_cast<long long>(T + N_AQ) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_cond;
-    CK(vla::gemm_launch(g, s, &_err));
-    // K|V of the NP raw rows -> kv rows [T+65, NK); K columns scaled by tanh(gating_factor) (AH:269 / AH:391)
-    g = vla::GemmArgs();
-    g.A = hs; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM; g.rows = NP; g.batches = B;
-    g.W = w.wkv_vis; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
-    g.C = e->h_kv + static_cast<long long>(T + N_AQ + 1) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV;
-    g.bias = w.bkv_vis; g.colscale = w.gatevec;
+    g.C = kvb + static_cast<long long>(T + N_AQ) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_cond;
     CK(vla::gemm_launch(g, s, &_err));
     // q and self K|V of the current x -> kv rows [0, T)
     g = vla::GemmArgs();
@@ -419,10 +482,10 @@ int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_
     g = vla::GemmArgs();
     g.A = e->head_x[i]; g.a_batch_stride = static_cast<long long>(T) * D_LLM; g.lda = D_LLM; g.rows = T; g.batches = B;
     g.W = w.wkv_self; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
-    g.C = e->h_kv; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_self;
+    g.C = kvb; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_self;
     CK(vla::gemm_launch(g, s, &_err));
-    if (pro) CK(vla::policy_rope_launch(e->h_q, e->h_kv, B, T, NP, e->prope_cos, e->prope_sin, s, &_err));
-    CK(vla::cross_attention_launch(e->h_q, D_LLM, T, e->h_kv, e->h_kv + D_LLM, PKV, NK, B, 8, 1, 112, 0, e->h_ao,
+    if (pro) CK(vla::policy_rope_launch(e->h_q, kvb, B, T, NP, e->prope_cos, e->prope_sin, s, &_err));
+    CK(vla::cross_attention_launch(e->h_q, D_LLM, T, kvb, kvb + D_LLM, PKV, NK, B, 8, 1, 112, 0, e->h_ao,
                                    D_LLM, s, &_err));
     g = vla::GemmArgs();
     g.A = e->h_ao; g.lda = D_LLM; g.rows = B * T; g.W = w.wo; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
@@ -662,12 +725,15 @@ int vla_finalize(vla_engine* e) {
     e->maxB = B; e->maxL = L; e->maxS = S;
     const size_t slabs = static_cast<size_t>(B) * n;
     const size_t Mv = slabs * TOK_DINO;
-    e->w_col = e->dalloc<bf16>(slabs * 256 * KP);
-    e->w_x = e->dalloc<bf16>(Mv * D_SIG);
-    e->w_xn = e->dalloc<bf16>(Mv * D_SIG);
-    e->w_qkv = e->dalloc<bf16>(Mv * 3 * D_SIG);
-    e->w_attn = e->dalloc<bf16>(Mv * D_SIG);
-    e->w_h = e->dalloc<bf16>(Mv * F_SIG);
+    for (int t = 0; t < 2; ++t) {
+      const size_t D = t == 0 ? D_DINO : D_SIG, F = t == 0 ? F_DINO : F_SIG;
+      e->tw[t].col = e->dalloc<bf16>(slabs * 256 * KP);
+      e->tw[t].x = e->dalloc<bf16>(Mv * D);
+      e->tw[t].xn = e->dalloc<bf16>(Mv * D);
+      e->tw[t].qkv = e->dalloc<bf16>(Mv * 3 * D);
+      e->tw[t].attn = e->dalloc<bf16>(Mv * D);
+      e->tw[t].h = e->dalloc<bf16>(Mv * F);
+    }
     e->w_patches = e->dalloc<bf16>(slabs * 256 * D_VIS);
     e->w_ph1 = e->dalloc<bf16>(slabs * 256 * D_PROJ1);
     e->w_ph2 = e->dalloc<bf16>(slabs * 256 * D_LLM);
@@ -682,6 +748,23 @@ int vla_finalize(vla_engine* e) {
     e->h_p1 = e->dalloc<bf16>(static_cast<size_t>(B) * D_LLM);
     e->h_p = e->dalloc<bf16>(static_cast<size_t>(B) * D_LLM);
     e->h_kv = e->dalloc<bf16>(static_cast<size_t>(B) * (e->T + N_AQ + 1 + e->NP) * PKV);
+    e->small_B = B < 8 ? B : 8;
+    if (getenv("VLA_NO_SIDE_STREAM")) e->small_B = 0;
+    if (e->small_B) {
+      for (int i = 0; i < 24; ++i)
+        e->h_kv_blk.push_back(e->dalloc<bf16>(static_cast<size_t>(e->small_B) * (e->T + N_AQ + 1 + e->NP) * PKV));
+      if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess)
+        return e->fail(VLA_ERR_CUDA, "side stream creation failed");
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
+      for (int i = 0; i < 24; ++i) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+        e->ev_layer.push_back(a);
+        e->ev_kv.push_back(b);
+      }
+    }
     e->h_q = e->dalloc<bf16>(BT * D_LLM);
     e->h_ao = e->dalloc<bf16>(BT * D_LLM);
     e->h_y = e->dalloc<bf16>(BT * D_LLM);
@@ -883,6 +966,11 @@ void vla_destroy(vla_engine* e) {
   if (e->gev_in) cudaEventDestroy(e->gev_in);
   if (e->gev_out) cudaEventDestroy(e->gev_out);
   if (e->gstream) cudaStreamDestroy(e->gstream);
+  for (cudaEvent_t ev : e->ev_layer) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->ev_kv) cudaEventDestroy(ev);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->side) cudaStreamDestroy(e->side);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
 }
