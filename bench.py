@@ -277,6 +277,20 @@ def main():
     d2h = 2 * on_h.numel() * 4 + 4
     assert torch.equal(ou_h, out.cpu()), "host-path result differs from device-path result"
 
+    # the same end-to-end call from uint8 frames (device-side ToTensor + Normalize): 4x fewer H2D bytes
+    g8 = torch.Generator().manual_seed(99 + rank)
+    img_h = torch.randint(0, 256, (B, N_IMAGES, 224, 224, 3), generator=g8, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        eng.predict_host_u8(img_h, ext_h, aq_h, prop_h, on_h, ou_h)
+    sync_all()
+    e0.record()
+    for _ in range(K):
+        eng.predict_host_u8(img_h, ext_h, aq_h, prop_h, on_h, ou_h)
+    e1.record()
+    sync_all()
+    ms_e2e_u8 = reduce_max(e0.elapsed_time(e1) / K)
+    h2d_u8 = img_h.numel() + ext_h.numel() * 8 + aq_h.numel() * 4 + prop_h.numel() * 4
+
     # ---------------- roofline of the dominant kernel: tcgen05 GEMM, timed per launch with CUDA events
     lib.vla_profile_gemm(1)
     step_device()
@@ -356,6 +370,9 @@ def main():
             "clocks": clk.summary(),
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_uint8_frames": {"value": world * B / (ms_e2e_u8 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_u8,
+                                 "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                                 "note": "vla_predict_host_u8: uint8 HWC frames, normalisation on the device"},
             "gpu_launches": int(launches),
             "roofline": roofline, "step_roofline": step_roofline, "latency_bs1": latency,
         }

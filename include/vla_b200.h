@@ -109,6 +109,23 @@ int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext
                      const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm,
                      float* out_unnorm, void* out_last_ha, void* stream);
 
+/* Device-side image front-end: the same forward from uint8 frames.  `images` is
+ * (B, n_images, 224, 224, 3) uint8, HWC, already resized / centre-cropped like PrismaticImageProcessor.apply_transform
+ * does on the CPU (prismatic/extern/hf/processing_prismatic.py:128-145); the per-backbone ToTensor + Normalize and the
+ * bf16 cast of get_vla_action (experiments/robot/openvla_utils.py:786-796) are applied on the device through a table
+ * built with the processor's fp32 arithmetic, so results are bit-identical to feeding the CPU-normalised pixel_values
+ * to vla_predict.  vla_predict_u8 takes device pointers, vla_predict_host_u8 host pointers (H2D / D2H inside). */
+int vla_predict_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids, const int32_t* aq_index,
+                   const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
+                   void* stream);
+int vla_predict_host_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids, const int32_t* aq_index,
+                        const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
+                        void* stream);
+/* Normalisation statistics of the two backbones, mean[2][3] / std[2][3] (backbone 0 = DINOv2, 1 = SigLIP; the
+ * defaults are those of pretrained_models/configs/preprocessor_config.json).  May be called before or after
+ * vla_finalize. */
+int vla_set_image_norm(vla_engine* e, const float* mean, const float* stdv);
+
 /* Debug taps for parity tests: copies an intermediate of the LAST vla_predict call to `dst`
  * (device or host).  Names: "patches" (B,NP,2176) tower output, "projected" (B,NP,896),
  * "llm_in" (B,S,896), "hidden.<i>" i in 1..24 (B,S,896) as returned by HF output_hidden_states,

@@ -110,6 +110,41 @@ def test_engine_graph_replay_is_deterministic():
     assert not torch.equal(changed, outs[0])
 
 
+def test_uint8_front_end_is_bit_identical():
+    """uint8 HWC frames through the device-side ToTensor + Normalize + bf16 cast give exactly the
+    result of the reference's CPU normalisation (processing_prismatic.py:128-145) fed as pixel_values."""
+    from vla_adapter_b200.engine import VLAEngine
+
+    cfg = O.OracleConfig(n_images=2, dino_depth=3, siglip_depth=3, vocab_size=2048, pro=True)
+    W = O.make_weights(cfg, seed=2)
+    _, ids, prop = O.make_inputs(cfg, 3, 21, seed=2)
+    g = torch.Generator().manual_seed(7)
+    img = torch.randint(0, 256, (3, 2, 224, 224, 3), generator=g, dtype=torch.uint8)
+    img[0, 0, :2] = torch.arange(256, dtype=torch.uint8).repeat(2 * 224 * 3)[:2 * 224 * 3].view(2, 224, 3)  # every level
+    # the processor: ToTensor (/255), Normalize per backbone, channel-stack [DINOv2 | SigLIP] per image, bf16
+    x = img.permute(0, 1, 4, 2, 3).to(torch.float32).div(255)
+    m0 = torch.tensor([0.485, 0.456, 0.406]).view(1, 1, 3, 1, 1)
+    s0 = torch.tensor([0.229, 0.224, 0.225]).view(1, 1, 3, 1, 1)
+    pix = torch.cat([x.sub(m0).div(s0), x.sub(0.5).div(0.5)], dim=2).reshape(3, 12, 224, 224).to(torch.bfloat16)
+    eng = VLAEngine(n_images=2, pro=True, dino_depth=3, siglip_depth=3, vocab_size=2048, max_batch=3, max_prompt_len=21)
+    eng.load_flat(W)
+    eng.finalize()
+    a_ref, n_ref, h_ref = eng.predict_action_batch(ids, None, pix, prop, return_hidden=True)
+    a_u8, n_u8, h_u8 = eng.predict_action_batch(ids, None, None, prop, return_hidden=True, images_u8=img)
+    patches_equal = True
+    eng.close()
+    assert np.array_equal(n_ref, n_u8) and np.array_equal(a_ref, a_u8)
+    assert torch.equal(h_ref, h_u8)
+    with pytest.raises(ValueError):
+        eng2 = VLAEngine(n_images=1, dino_depth=2, siglip_depth=2, vocab_size=64, max_batch=1, max_prompt_len=8)
+        try:
+            eng2.predict_host_u8(torch.zeros(1, 1, 224, 224, 3), torch.zeros(1, 73, dtype=torch.int64),
+                                 torch.zeros(1, 73, dtype=torch.int32), torch.zeros(1, 8), torch.zeros(1, 8, 7),
+                                 torch.zeros(1, 8, 7))
+        finally:
+            eng2.close()
+
+
 def test_base_rows_identical_and_causal_invariants():
     """Reference properties: base head has no positional signal, so all T rows agree."""
     cfg, truth, ref16, normalized, actions, ha, got, _ = _run_case(False, 2, 2, 17, seed=3)

@@ -103,6 +103,7 @@ struct vla_engine {
   bf16 *x0, *head_fc2_w, *pp_w1, *pp_w2;
   float *head_ln2w, *head_ln2b, *head_fc2_b, *pp_b1, *pp_b2;
   float *prope_cos = nullptr, *prope_sin = nullptr;
+  bf16* img_lut = nullptr;  // [2 towers][3 channels][256]: ToTensor + Normalize + bf16 of a uint8 pixel
   float *st_hi = nullptr, *st_lo = nullptr;
   uint8_t* st_mask = nullptr;
   bool stats_set = false;
@@ -129,6 +130,7 @@ struct vla_engine {
   // pinned/dev staging for vla_predict_host
   void *pin_pix = nullptr, *pin_ids = nullptr, *pin_aq = nullptr, *pin_prop = nullptr, *pin_out = nullptr,
        *pin_ha = nullptr;
+  void *pin_u8 = nullptr, *dev_u8 = nullptr;
   void *dev_pix = nullptr, *dev_ids = nullptr, *dev_aq = nullptr, *dev_prop = nullptr, *dev_out = nullptr,
        *dev_ha = nullptr;
 
@@ -140,10 +142,10 @@ struct vla_engine {
   // key (the first runs eagerly and performs the one-time cudaFuncSetAttribute calls).  Replayed on an internal
   // stream fenced to the caller's stream with events, so the legacy default stream works too.
   struct GraphKey {
-    int B, L;
+    int B, L, u8;
     const void *pix, *ids, *aq, *prop, *out_norm, *out_unnorm, *out_ha;
     bool operator==(const GraphKey& o) const {
-      return B == o.B && L == o.L && pix == o.pix && ids == o.ids && aq == o.aq && prop == o.prop &&
+      return B == o.B && L == o.L && u8 == o.u8 && pix == o.pix && ids == o.ids && aq == o.aq && prop == o.prop &&
              out_norm == o.out_norm && out_unnorm == o.out_unnorm && out_ha == o.out_ha;
     }
   };
@@ -276,12 +278,14 @@ void build_tower(vla_engine* e, Tower& t, const std::string& pfx, bool is_dino, 
     if (_rc) return e->fail(_rc, _err ? _err : "kernel launch failed"); \
   } while (0)
 
-int run_tower(vla_engine* e, const Tower& t, const bf16* pix, int B, int tower_idx, cudaStream_t s) {
+int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix_u8, int B, int tower_idx,
+              cudaStream_t s) {
   const int n = e->cfg.n_images, slabs = B * n, D = t.D, F = t.F;
   const int M = slabs * t.tokens;
   const vla_engine::TowerWs& ws = e->tw[tower_idx];
   bf16* x = ws.x;
-  CK(vla::im2col_launch(pix, B, n, tower_idx, ws.col, s, &_err));
+  if (pix_u8) CK(vla::im2col_u8_launch(pix_u8, B, n, tower_idx, e->img_lut, ws.col, s, &_err));
+  else CK(vla::im2col_launch(pix, B, n, tower_idx, ws.col, s, &_err));
   if (t.prefix) CK(vla::prefix_tokens_launch(x, slabs, static_cast<long long>(t.tokens) * D, D, t.prefix_rows, t.prefix, s, &_err));
   {
     // patch embed (+bias +pos_embed) written behind the prefix rows of every image slab
@@ -363,7 +367,7 @@ int policy_kv_from_llm(vla_engine* e, int i, const bf16* hs, int B, int L, cudaS
   return 0;
 }
 
-int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_t* aq_index, const float* proprio,
+int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t* ext_ids, const int32_t* aq_index, const float* proprio,
             int B, int L, float* out_norm, float* out_unnorm, bf16* out_last_ha, cudaStream_t s) {
   const int NP = e->NP, T = e->T, A = e->A, P = e->P;
   vla::pdl_set(B <= 8);  // programmatic dependent launch pays off only when kernels are a few microseconds long
@@ -382,9 +386,9 @@ int forward(vla_engine* e, const bf16* pix, const int64_t* ext_ids, const int32_
     if (cudaEventRecord(e->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(s2, e->ev_fork, 0) != cudaSuccess)
       return e->fail(VLA_ERR_CUDA, "side stream fork failed");
   }
-  int rc = run_tower(e, e->dino, pix, B, 0, s2);  // the shorter tower rides on the side stream
+  int rc = run_tower(e, e->dino, pix, pix_u8, B, 0, s2);  // the shorter tower rides on the side stream
   if (rc) return rc;
-  rc = run_tower(e, e->sig, pix, B, 1, s);
+  rc = run_tower(e, e->sig, pix, pix_u8, B, 1, s);
   if (rc) return rc;
   if (small) {
     if (cudaEventRecord(e->ev_join, s2) != cudaSuccess || cudaStreamWaitEvent(s, e->ev_join, 0) != cudaSuccess)
@@ -627,6 +631,11 @@ int vla_finalize(vla_engine* e) {
       int rc = vla_set_action_stats(e, hi.data(), lo.data(), nullptr);
       if (rc) return rc;
     }
+    if (!e->img_lut) {  // preprocessor_config.json: DINOv2 = ImageNet statistics, SigLIP = 0.5 / 0.5
+      const float mean[6] = {0.485f, 0.456f, 0.406f, 0.5f, 0.5f, 0.5f}, stdv[6] = {0.229f, 0.224f, 0.225f, 0.5f, 0.5f, 0.5f};
+      int rc = vla_set_image_norm(e, mean, stdv);
+      if (rc) return rc;
+    }
     build_tower(e, e->dino, "vla.vision_backbone.featurizer.", true, c.dino_depth);
     build_tower(e, e->sig, "vla.vision_backbone.fused_featurizer.", false, c.siglip_depth);
     e->pj_w1 = e->pack("vla.projector.fc1.weight", D_PROJ1, D_VIS);
@@ -792,9 +801,9 @@ int vla_finalize(vla_engine* e) {
   return VLA_OK;
 }
 
-int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids, const int32_t* aq_index,
-                const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
-                void* stream) {
+static int predict_impl(vla_engine* e, const void* pixel_values, int is_u8, const int64_t* ext_ids,
+                        const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm, float* out_unnorm,
+                        void* out_last_ha, void* stream) {
   if (!e) return VLA_ERR_INVALID;
   if (!e->finalized) return e->fail(VLA_ERR_NOT_FINALIZED, "vla_predict before vla_finalize");
   if (!pixel_values || !ext_ids || !aq_index || !proprio || !out_norm)
@@ -802,12 +811,13 @@ int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
   if (B < 1 || B > e->maxB) return e->fail(VLA_ERR_INVALID, "vla_predict: batch outside [1, max_batch]");
   if (L < 1 || L > e->maxL) return e->fail(VLA_ERR_INVALID, "vla_predict: prompt length outside [1, max_prompt_len]");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bf16* pix = static_cast<const bf16*>(pixel_values);
+  const bf16* pix = is_u8 ? nullptr : static_cast<const bf16*>(pixel_values);
+  const uint8_t* pix8 = is_u8 ? static_cast<const uint8_t*>(pixel_values) : nullptr;
   bf16* ha = static_cast<bf16*>(out_last_ha);
   int rc = 0;
   vla_engine::GraphEntry* ge = nullptr;
   if (e->use_graphs && !vla::gemm_profile_enabled()) {
-    const vla_engine::GraphKey key{B, L, pixel_values, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha};
+    const vla_engine::GraphKey key{B, L, is_u8, pixel_values, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha};
     for (auto& g : e->graphs)
       if (g.key == key) ge = &g;
     if (!ge) {
@@ -833,7 +843,7 @@ int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
       const long long before = vla::gemm_launch_count() + vla::ops_launch_count();
       if (cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
         return e->fail(VLA_ERR_CUDA, "cudaStreamBeginCapture failed");
-      rc = forward(e, pix, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, ha, e->gstream);
+      rc = forward(e, pix, pix8, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, ha, e->gstream);
       const cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
       ge->launches = vla::gemm_launch_count() + vla::ops_launch_count() - before;
       if (rc) {
@@ -854,7 +864,7 @@ int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
     e->last_launches = ge->launches;
   } else {
     const long long before = vla::gemm_launch_count() + vla::ops_launch_count();
-    rc = forward(e, pix, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, ha, s);
+    rc = forward(e, pix, pix8, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, ha, s);
     e->last_launches = vla::gemm_launch_count() + vla::ops_launch_count() - before;
   }
   e->lastB = B;
@@ -862,9 +872,46 @@ int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
   return rc;
 }
 
-int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext_ids, const int32_t* aq_index,
-                     const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
-                     void* stream) {
+int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids, const int32_t* aq_index,
+                const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
+                void* stream) {
+  return predict_impl(e, pixel_values, 0, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, out_last_ha, stream);
+}
+
+int vla_predict_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids, const int32_t* aq_index,
+                   const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
+                   void* stream) {
+  return predict_impl(e, images, 1, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, out_last_ha, stream);
+}
+
+int vla_set_image_norm(vla_engine* e, const float* mean, const float* stdv) {
+  if (!e) return VLA_ERR_INVALID;
+  if (!mean || !stdv) return e->fail(VLA_ERR_INVALID, "set_image_norm: null statistics");
+  // ToTensor (u8 / 255), Normalize ((x - mean) / std) in fp32 like torchvision, then the bf16 cast of the caller
+  std::vector<bf16> lut(2 * 3 * 256);
+  for (int t = 0; t < 2; ++t)
+    for (int c = 0; c < 3; ++c) {
+      if (!(stdv[t * 3 + c] > 0.f)) return e->fail(VLA_ERR_INVALID, "set_image_norm: std must be positive");
+      for (int v = 0; v < 256; ++v) {
+        volatile float x = static_cast<float>(v) / 255.0f;
+        volatile float y = x - mean[t * 3 + c];
+        volatile float z = y / stdv[t * 3 + c];
+        lut[(t * 3 + c) * 256 + v] = __float2bfloat16_rn(z);
+      }
+    }
+  try {
+    if (!e->img_lut) e->img_lut = e->dalloc<bf16>(lut.size());
+  } catch (const std::exception& ex) {
+    return e->fail(VLA_ERR_CUDA, ex.what());
+  }
+  if (cudaMemcpy(e->img_lut, lut.data(), lut.size() * sizeof(bf16), cudaMemcpyHostToDevice) != cudaSuccess)
+    return e->fail(VLA_ERR_CUDA, "set_image_norm: copy failed");
+  return VLA_OK;
+}
+
+static int predict_host_impl(vla_engine* e, const void* pixel_values, int is_u8, const int64_t* ext_ids,
+                             const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm,
+                             float* out_unnorm, void* out_last_ha, void* stream) {
   if (!e) return VLA_ERR_INVALID;
   if (!e->finalized) return e->fail(VLA_ERR_NOT_FINALIZED, "vla_predict_host before vla_finalize");
   if (!pixel_values || !ext_ids || !aq_index || !proprio || !out_norm)
@@ -893,14 +940,17 @@ int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext
   const int Lext = L + N_AQ + 1;
   const size_t n_out = static_cast<size_t>(B) * e->T * e->A;
   cudaError_t ce = cudaSuccess;
-  ce = cudaMemcpyAsync(e->dev_pix, pixel_values, static_cast<size_t>(B) * 6 * e->cfg.n_images * 224 * 224 * 2, cudaMemcpyHostToDevice, s);
+  // uint8 frames are a quarter of the bf16 pixel_values (3 bytes per pixel instead of 2 towers x 3 channels x 2 bytes)
+  const size_t in_bytes = is_u8 ? static_cast<size_t>(B) * e->cfg.n_images * 224 * 224 * 3
+                                : static_cast<size_t>(B) * 6 * e->cfg.n_images * 224 * 224 * 2;
+  ce = cudaMemcpyAsync(e->dev_pix, pixel_values, in_bytes, cudaMemcpyHostToDevice, s);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_ids, ext_ids, static_cast<size_t>(B) * Lext * 8, cudaMemcpyHostToDevice, s);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_aq, aq_index, static_cast<size_t>(B) * Lext * 4, cudaMemcpyHostToDevice, s);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_prop, proprio, static_cast<size_t>(B) * e->P * 4, cudaMemcpyHostToDevice, s);
   if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(ce));
   float* d_norm = static_cast<float*>(e->dev_out);
   float* d_un = d_norm + static_cast<size_t>(e->maxB) * e->T * e->A;
-  int rc = vla_predict(e, e->dev_pix, static_cast<const int64_t*>(e->dev_ids), static_cast<const int32_t*>(e->dev_aq),
+  int rc = predict_impl(e, e->dev_pix, is_u8, static_cast<const int64_t*>(e->dev_ids), static_cast<const int32_t*>(e->dev_aq),
                        static_cast<const float*>(e->dev_prop), B, L, d_norm, d_un, out_last_ha ? e->dev_ha : nullptr, stream);
   if (rc) return rc;
   ce = cudaMemcpyAsync(out_norm, d_norm, n_out * 4, cudaMemcpyDeviceToHost, s);
@@ -916,6 +966,18 @@ int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext
     return e->fail(VLA_ERR_INVALID, flag == 1 ? "token id outside [0, vocab_size)" : "ActionQuery index outside [0, 64)");
   }
   return VLA_OK;
+}
+
+int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext_ids, const int32_t* aq_index,
+                     const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
+                     void* stream) {
+  return predict_host_impl(e, pixel_values, 0, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, out_last_ha, stream);
+}
+
+int vla_predict_host_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids, const int32_t* aq_index,
+                        const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
+                        void* stream) {
+  return predict_host_impl(e, images, 1, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, out_last_ha, stream);
 }
 
 int vla_get_tap(vla_engine* e, const char* name, void* dst, size_t capacity, size_t* bytes) {

@@ -171,6 +171,38 @@ rope_apply_kernel(__nv_bfloat16* __restrict__ x, int ld, int off, int n_heads, l
                                                  pack_bf16(o2[4], o2[5]), pack_bf16(o2[6], o2[7]));
 }
 
+// ------------------------------------------------------------------ im2col straight from uint8 frames
+// Device-side image front-end: frames already resized / centre-cropped to 224x224 arrive as uint8 HWC
+// (PIL layout); the processor's ToTensor + Normalize of this tower (processing_prismatic.py:128-145, means / stds of
+// preprocessor_config.json) and the cast to bf16 are a 3 x 256 lookup table built on the host with the processor's
+// own fp32 arithmetic, so the result is bit-identical to the CPU path while the H2D copy shrinks 4x.
+__global__ void __launch_bounds__(256)
+im2col_u8_kernel(const uint8_t* __restrict__ img, int n_img, int tower, long long n_slabs,
+                 const __nv_bfloat16* __restrict__ lut /*[2][3][256]*/, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int KP = 592;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = n_slabs * 256 * 43;  // 42 (c,ky) segments + 1 zero-pad segment
+  if (idx >= total) return;
+  const int seg = static_cast<int>(idx % 43);
+  const long long pr = idx / 43;  // slab*256 + patch
+  const int patch = static_cast<int>(pr & 255);
+  const long long slab = pr >> 8;
+  __nv_bfloat16* orow = out + pr * KP;
+  if (seg == 42) {
+    *reinterpret_cast<uint2*>(orow + 588) = make_uint2(0u, 0u);
+    return;
+  }
+  const int c = seg / 14, ky = seg - c * 14;
+  const int py = patch >> 4, px = patch & 15;
+  const uint8_t* src = img + ((slab * 224 + (py * 14 + ky)) * 224LL + px * 14) * 3 + c;  // HWC
+  const __nv_bfloat16* t = lut + (tower * 3 + c) * 256;
+  __nv_bfloat16* dst = orow + c * 196 + ky * 14;
+#pragma unroll
+  for (int i = 0; i < 14; ++i) dst[i] = t[__ldg(src + i * 3)];
+}
+
 // ------------------------------------------------------------------ im2col for the 14x14/14 patch conv
 // One thread per (patch row vector of 14 pixels): reads 14 contiguous bf16 (28 B) of the image, writes
 // them at k = c*196 + ky*14 + [0,14).  Grid: (image slab, patch) x (c, ky).
@@ -390,6 +422,15 @@ int rope_launch(__nv_bfloat16* x, int ld, int off, int n_heads, int B, int S, fl
   if (!rc) rc = rope_apply_launch(x, ld, off, n_heads, B, S, tab, tab + S * 32, s, err);
   cudaFreeAsync(tab, s);
   return rc;
+}
+
+int im2col_u8_launch(const uint8_t* img, int B, int n_img, int tower, const __nv_bfloat16* lut, __nv_bfloat16* out,
+                     cudaStream_t s, const char** err) {
+  const long long n_slabs = static_cast<long long>(B) * n_img;
+  const long long total = n_slabs * 256 * 43;
+  launch_kernel(im2col_u8_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, img, n_img, tower, n_slabs,
+                lut, out);
+  return check_launch(err);
 }
 
 int im2col_launch(const __nv_bfloat16* pix, int B, int n_img, int tower, __nv_bfloat16* out, cudaStream_t s,

@@ -55,6 +55,11 @@ void attention_set_impl(int impl);
 int im2col_launch(const __nv_bfloat16* pix, int B, int n_img, int tower, __nv_bfloat16* out, cudaStream_t s,
                   const char** err);
 
+// Same, from uint8 HWC frames (B, n_img, 224, 224, 3): value = lut[tower][c][u8] (ToTensor + Normalize + bf16 cast
+// tabulated by the host; lut is [2][3][256] bf16).
+int im2col_u8_launch(const uint8_t* img, int B, int n_img, int tower, const __nv_bfloat16* lut, __nv_bfloat16* out,
+                     cudaStream_t s, const char** err);
+
 // Writes the DINOv2 prefix rows (cls + 4 register tokens, no pos-embed) of every image slab.
 int prefix_tokens_launch(__nv_bfloat16* x, int n_slabs, long long slab_stride, int dim,
                          const __nv_bfloat16* prefix /*[5, dim]*/, int n_prefix, cudaStream_t s,

@@ -207,18 +207,45 @@ class VLAEngine:
                                        torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, self._h)
 
+    def predict_host_u8(self, images_u8: torch.Tensor, ext_ids: torch.Tensor, aq_index: torch.Tensor,
+                        proprio: torch.Tensor, out_norm: torch.Tensor, out_unnorm: torch.Tensor,
+                        out_last_ha: Optional[torch.Tensor] = None) -> None:
+        """predict_host from uint8 frames (B, n_images, 224, 224, 3), HWC, already resized / centre-cropped: the
+        processor's ToTensor + Normalize + bf16 cast happen on the device (bit-identical to the CPU path)."""
+        B, Lext = ext_ids.shape
+        if images_u8.dtype != torch.uint8 or tuple(images_u8.shape) != (B, self.n_images, 224, 224, 3):
+            raise ValueError(f"images must be uint8 ({B}, {self.n_images}, 224, 224, 3), got {images_u8.dtype} "
+                             f"{tuple(images_u8.shape)}")
+        images_u8 = images_u8.contiguous()
+        rc = self.lib.vla_predict_host_u8(self._h, images_u8.data_ptr(), ext_ids.data_ptr(), aq_index.data_ptr(),
+                                          proprio.data_ptr(), B, Lext - NUM_TOKENS - 1, out_norm.data_ptr(),
+                                          out_unnorm.data_ptr(),
+                                          out_last_ha.data_ptr() if out_last_ha is not None else None,
+                                          torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, self._h)
+
+    def set_image_norm(self, mean, std) -> None:
+        """mean / std of the two backbones, each (2, 3): row 0 DINOv2, row 1 SigLIP (preprocessor_config.json)."""
+        import ctypes as C
+        m = (C.c_float * 6)(*[float(v) for row in mean for v in row])
+        sd = (C.c_float * 6)(*[float(v) for row in std for v in row])
+        _lib.check(self.lib.vla_set_image_norm(self._h, m, sd), self._h)
+
     def predict_action_batch(self, input_ids, attention_mask=None, pixel_values=None, proprio=None,
-                             unnorm_key=None, return_hidden: bool = False):
+                             unnorm_key=None, return_hidden: bool = False, images_u8=None):
         """(B, L) ids + (B, 6n, 224, 224) pixels + (B, P) proprio -> un-normalised actions (B, T, A) float64
         and normalised actions (B, T, A) float32 [+ last-layer ActionQuery states (B, 1, 64, D) bf16]."""
         if not self._finalized:
             raise RuntimeError("engine not finalized")
         ext, aq = self._prep(input_ids, attention_mask)
         B = ext.shape[0]
-        pix = torch.as_tensor(pixel_values)
+        if (pixel_values is None) == (images_u8 is None):
+            raise ValueError("pass exactly one of pixel_values (normalised, like the reference) or images_u8")
+        pix = torch.as_tensor(pixel_values if images_u8 is None else images_u8)
         if pix.shape[0] != B:
             raise ValueError("Non-homogenous batch of (text, image) input -- forward() does not support mixed batches!")
-        pix = pix.to(torch.bfloat16).contiguous()
+        if images_u8 is None:
+            pix = pix.to(torch.bfloat16).contiguous()
         pr = torch.as_tensor(np.asarray(proprio.cpu() if torch.is_tensor(proprio) else proprio, dtype=np.float32))
         pr = pr.reshape(B, -1).contiguous()
         if pr.shape[1] != self.proprio_dim:
@@ -228,7 +255,10 @@ class VLAEngine:
         out_n = torch.empty((B, T, A), dtype=torch.float32)
         out_u = torch.empty((B, T, A), dtype=torch.float32)
         ha = torch.empty((B, NUM_TOKENS, LLM_DIM), dtype=torch.bfloat16) if return_hidden else None
-        self.predict_host(pix.cpu(), ext, aq, pr, out_n, out_u, ha)
+        if images_u8 is None:
+            self.predict_host(pix.cpu(), ext, aq, pr, out_n, out_u, ha)
+        else:
+            self.predict_host_u8(pix.cpu(), ext, aq, pr, out_n, out_u, ha)
         normalized = out_n.numpy()
         if self.norm_stats is not None:
             actions = self._unnormalize_actions(normalized.astype(np.float32), unnorm_key)
