@@ -181,7 +181,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=200.0, help="wall-clock bound [s] of the reference arm")
     ap.add_argument("--latency-iters", type=int, default=30)
+    ap.add_argument("--chunk", default="8x7x8", help="chunk_len x action_dim x proprio_dim: 8x7x8 = LIBERO / CALVIN "
+                    "(constants.py:28-40), 25x14x14 = the reference's larger-chunk preset (ALOHA, constants.py:42-47)")
     args = ap.parse_args()
+    global T_CHUNK, A_DIM, P_DIM
+    T_CHUNK, A_DIM, P_DIM = (int(v) for v in args.chunk.split("x"))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
 
@@ -210,7 +214,7 @@ def main():
     eng = VLAEngine(n_images=N_IMAGES, chunk_len=T_CHUNK, action_dim=A_DIM, proprio_dim=P_DIM, pro=pro, max_batch=B,
                     max_prompt_len=L, device=local,
                     norm_stats={"synthetic": {"action": {"q01": [-1.0] * A_DIM, "q99": [1.0] * A_DIM,
-                                                         "mask": [True] * 6 + [False]}}})
+                                                         "mask": [True] * (A_DIM - 1) + [False]}}})
     n_params = load_random_weights(eng, seed=0, n_images=N_IMAGES, action_dim=A_DIM, proprio_dim=P_DIM, pro=pro)
     eng.finalize()
     lib = _lib.load()
