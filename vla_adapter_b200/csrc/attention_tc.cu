@@ -183,13 +183,20 @@ VLA_DEVINL void named_bar_sync(int id, int nthreads) {
 template <int HD, int NLIVE, bool MASKED>
 VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint32_t tO, int k0h, int grow, int j, int half,
                                 float sl2, float& m_ref, float& l, float* xch_mine, const float* xch_other, int bar_id,
-                                uint32_t turn_wait, uint32_t turn_parity, uint32_t turn_arrive) {
+                                uint32_t turn_wait, uint32_t turn_parity, uint32_t turn_arrive, uint32_t s_free_bar,
+                                uint32_t pv_done_bar, uint32_t pv_parity) {
   uint32_t v[NLIVE > 0 ? NLIVE : 1][32];
   float mloc = -INFINITY;
   if (NLIVE > 0) {
 #pragma unroll
     for (int c = 0; c < NLIVE; ++c) tmem_ld_32x32b_x32(tSh + c * 32, v[c]);
     tmem_ld_wait();
+  }
+  if (s_free_bar) {  // the scores are in registers: the MMA warp may overwrite S with the next tile's Q K^T
+    tc_fence_before();
+    mbar_arrive(s_free_bar);
+  }
+  if (NLIVE > 0) {
     if (MASKED) {  // the half touches the causal diagonal or the end of the keys: straight-line select on every element
       int last = p.Skv - 1;                        // last key this row may attend to ...
       if (p.causal && grow < last) last = grow;
@@ -216,6 +223,10 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
   *xch_mine = mloc;
   named_bar_sync(bar_id, 64);
   const float m_new = fmaxf(m_ref, fmaxf(mloc, *xch_other));
+  if (pv_done_bar) {  // PV of the previous tile has retired: O is stable and the P columns may be rewritten
+    mbar_wait(pv_done_bar, pv_parity);
+    tc_fence_after();
+  }
   if (j == 0) {
     m_ref = m_new;
   } else {
@@ -294,7 +305,13 @@ struct FaSmem {
   static constexpr uint32_t OFF_XCH = OFF_BAR + 256;  // row-max / row-sum exchange: [slot][parity][half][128] floats
   static constexpr uint32_t TOTAL = OFF_XCH + 2 * 2 * 2 * 128 * 4;  // the dynamic array is __align__(1024): no slack
   // TMEM columns: S_A [0,BN), S_B [BN,2BN) (P aliases the first half of S), then O_A, O_B
-  static constexpr uint32_t O_OFF = 2 * BN;
+  // Head dim 64 has room for P OUTSIDE the score columns (S_A S_B | P_A P_B | O_A O_B = 256 + 128 + 128): the next
+  // tile's QK^T is issued as soon as the softmax warps have read the scores, and PV of this tile runs beside the
+  // next tile's softmax.  Head dim 72 (2 x 80 accumulator columns) keeps P aliased over S.
+  static constexpr bool DEALIAS = !TAIL;
+  static constexpr uint32_t P_OFF = DEALIAS ? 2 * BN : 0;           // + P_STRIDE * slot
+  static constexpr uint32_t P_STRIDE = DEALIAS ? 64 : BN;
+  static constexpr uint32_t O_OFF = DEALIAS ? 2 * BN + 128 : 2 * BN;
   static constexpr uint32_t O_STRIDE = TAIL ? 128 : 64;
   static constexpr uint32_t TMEM_COLS = 512;
   static_assert(!(TAIL && BN == 64), "head dim 72 needs 2*64 + 2*80 TMEM columns: use BN = 128");
@@ -323,9 +340,11 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   auto o_full = [&](int x) { return bar_base + 8u * (12 + x); };
   auto o_empty = [&](int x) { return bar_base + 8u * (14 + x); };
   auto turn = [&](int x) { return bar_base + 8u * (16 + x); };        // exp-phase turn taking between the slots
-  auto kv_full = [&](int s) { return bar_base + 8u * (18 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (18 + NS + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_BAR + 8 * (18 + 2 * NS));
+  auto s_free = [&](int x) { return bar_base + 8u * (18 + x); };      // scores read into registers (DEALIAS)
+  auto pv_done = [&](int x) { return bar_base + 8u * (20 + x); };     // PV of the previous tile retired (DEALIAS)
+  auto kv_full = [&](int s) { return bar_base + 8u * (22 + s); };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (22 + NS + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_BAR + 8 * (22 + 2 * NS));
 
   // shfl-broadcast warp index: the role branches are then provably warp-uniform, so the MMA warp's descriptor
   // arithmetic stays on the uniform datapath and tcgen05.mma issues at the hardware rate (scripts/ubench/mma3.cu)
@@ -342,6 +361,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(turn(x), 8);
+      mbar_init(s_free(x), 256);
+      mbar_init(pv_done(x), 1);
       mbar_init(s_full(x), 1);
       mbar_init(p_ready(x), 256);
       mbar_init(o_full(x), 1);
@@ -408,7 +429,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     }
   } else if (warp_idx == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp waits, one lane issues)
-    uint32_t kv_cnt = 0, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0}, o_cnt[2] = {0, 0};
+    uint32_t kv_cnt = 0, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0}, o_cnt[2] = {0, 0}, f_cnt[2] = {0, 0};
     unsigned int tr_cnt = 0;
     const uint32_t idesc_pv = make_idesc_bf16(128, 64) | (1u << 16);
     const uint32_t idesc_pvt = make_idesc_bf16(128, 16) | (1u << 16);
@@ -458,7 +479,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       auto issue_pv = [&](int x, int j) {
         const int s = stage_of(j);
         const int n16 = n16_of(j);
-        const uint32_t tS = tmem_base + static_cast<uint32_t>(BN) * x, tO = tmem_base + L::O_OFF + L::O_STRIDE * x;
+        const uint32_t tS = tmem_base + L::P_OFF + L::P_STRIDE * x;  // P columns (over S unless de-aliased)
+        const uint32_t tO = tmem_base + L::O_OFF + L::O_STRIDE * x;
         const uint32_t sv = sbase + L::OFF_V + s * L::KV_TILE;
         if (elect_one()) {
           if (!(p.debug & 2)) {
@@ -485,6 +507,17 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         issue_qk(x, 0);
       }
       for (int j = 0; j < it.nmax; ++j) {
+        if (L::DEALIAS) {
+          // the next tile's scores as soon as this tile's have been read: S(j+1) is ready before softmax(j) ends
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            if (j >= it.n[x]) continue;
+            mbar_wait(s_free(x), f_cnt[x] & 1u);
+            ++f_cnt[x];
+            tc_fence_after();
+            if (j + 1 < it.n[x] && !(p.debug & 16)) issue_qk(x, j + 1);
+          }
+        }
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
           if (j >= it.n[x]) continue;
@@ -495,7 +528,13 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           tc_fence_after();
           issue_pv(x, j);
           if (j + 1 < it.n[x]) {
-            issue_qk(x, j + 1);  // in-order after PV(j): S_x / P_x is free again
+            if (L::DEALIAS) {
+              if (elect_one()) umma_commit(pv_done(x));  // P_x / O_x may be touched again by the softmax warps
+              __syncwarp();
+              if (p.debug & 16) issue_qk(x, j + 1);  // (experiment: no early issue)
+            } else {
+              issue_qk(x, j + 1);  // in-order after PV(j): S_x / P_x is free again
+            }
           } else {
             if (elect_one()) umma_commit(o_full(x));
             __syncwarp();
@@ -520,11 +559,12 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     const int row = quarter * 32 + lane;
     const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(BN) * x;
     const uint32_t tO = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + L::O_OFF + L::O_STRIDE * x;
-    const uint32_t tSh = tS + 64u * half, tPh = tS + 32u * half;
+    const uint32_t tP = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + L::P_OFF + L::P_STRIDE * x;
+    const uint32_t tSh = tS + 64u * half, tPh = tP + 32u * half;
     float* xch = reinterpret_cast<float*>(smem + L::OFF_XCH) + x * 512;  // [parity][half][128]
     const int bar_id = 1 + x * 4 + quarter;
     const float sl2 = p.scale_log2;
-    uint32_t s_cnt = 0, o_cnt = 0, x_cnt = 0, t_cnt = 0;
+    uint32_t s_cnt = 0, o_cnt = 0, x_cnt = 0, t_cnt = 0, d_cnt = 0;
     unsigned int tr_cnt = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const FaItem it = fa_decode(p, item);
@@ -570,14 +610,18 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           const bool do_arrive = pp && (x == 0 ? (j < m_pp) : (j + 1 < m_pp));
           const uint32_t t_wait = do_wait ? turn(x) : 0u, t_par = t_cnt & 1u, t_arr = do_arrive ? turn(x ^ 1) : 0u;
           if (do_wait) ++t_cnt;
+          // de-aliased P: announce "scores read" after the TMEM loads, wait for PV(j-1) before touching O / P
+          const uint32_t f_bar = L::DEALIAS ? s_free(x) : 0u;
+          const uint32_t d_bar = (L::DEALIAS && j > 0) ? pv_done(x) : 0u, d_par = d_cnt & 1u;
+          if (L::DEALIAS && j > 0) ++d_cnt;
           if (my_live == 2) {
-            if (masked) fa_softmax_tile<HD, 2, true>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
-            else fa_softmax_tile<HD, 2, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
+            if (masked) fa_softmax_tile<HD, 2, true>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            else fa_softmax_tile<HD, 2, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           } else if (my_live == 1) {
-            if (masked) fa_softmax_tile<HD, 1, true>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
-            else fa_softmax_tile<HD, 1, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
+            if (masked) fa_softmax_tile<HD, 1, true>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            else fa_softmax_tile<HD, 1, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           } else {
-            fa_softmax_tile<HD, 0, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr);
+            fa_softmax_tile<HD, 0, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           }
           if (my_live < my_all) {  // causal chunks above the diagonal: P = 0
             uint32_t z[16];
@@ -586,6 +630,16 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             for (int c = my_live; c < my_all; ++c) tmem_st_32x32b_x16(tPh + c * 16, z);
           }
           tmem_st_wait();
+        } else if (L::DEALIAS) {
+          // Padding-only warps keep the barriers moving, in step: with early QK issue s_full(j+1) can complete before
+          // the working warps have finished tile j, and an arrival on p_ready for tile j+1 made before phase j
+          // completes would be counted for phase j.  Waiting for PV(j-1) (issued after p_ready(j-1) completed)
+          // pins the order.
+          mbar_arrive(s_free(x));
+          if (j > 0) {
+            mbar_wait(pv_done(x), d_cnt & 1u);
+            ++d_cnt;
+          }
         }
         tc_fence_before();
         if (quarter == 0 && half == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 500 + x * 10 + j);
