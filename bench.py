@@ -320,6 +320,23 @@ def main():
                 "launches_per_step": int(g_n.value), "avg_launch_ms": g_ms.value / max(1, g_n.value),
                 "gemm_ms_per_step": g_ms.value, "gemm_share_of_step": g_ms.value / ms_step,
                 "algorithmic_gflop_per_sample": alg}
+    # per-subsystem device time of one eager step (events at the subsystem boundaries inside the engine)
+    seg3 = (C.c_float * 3)()
+    lib.vla_segment_timing(eng._h, 1)
+    step_device()
+    step_device()
+    torch.cuda.synchronize()
+    _lib.check(lib.vla_segment_times(eng._h, seg3), eng._h)
+    lib.vla_segment_timing(eng._h, 0)
+    NPt = 256 * N_IMAGES
+    fused_gf = alg["total"] - N_IMAGES * 382.77  # prefill + policy = total minus the towers/projector
+    segments = {"towers_projector_ms": seg3[0], "llm_prefill_ms": seg3[1], "policy_ms": seg3[2],
+                "prefill_policy": {"gflop_per_sample": fused_gf, "achieved": fused_gf * B / (seg3[1] + seg3[2]),
+                                   "peak": peak, "unit": "TFLOP/s",
+                                   "frac": fused_gf * B / (seg3[1] + seg3[2]) / peak,
+                                   "note": "north_star sub-path (Qwen prefill + Bridge-Attention policy), eager step"},
+                "towers_projector": {"achieved": N_IMAGES * 382.77 * B / seg3[0], "unit": "TFLOP/s",
+                                     "frac": N_IMAGES * 382.77 * B / seg3[0] / peak}}
     step_tflops = alg["total"] * B / ms_step
     step_roofline = {"achieved": step_tflops, "peak": peak, "unit": "TFLOP/s", "frac": step_tflops / peak,
                      "note": "whole step (all kernels) against the same measured dense-bf16 peak"}
@@ -378,7 +395,7 @@ def main():
                                  "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
                                  "note": "vla_predict_host_u8: uint8 HWC frames, normalisation on the device"},
             "gpu_launches": int(launches),
-            "roofline": roofline, "step_roofline": step_roofline, "latency_bs1": latency,
+            "roofline": roofline, "step_roofline": step_roofline, "segments": segments, "latency_bs1": latency,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

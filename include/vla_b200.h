@@ -126,6 +126,12 @@ int vla_predict_host_u8(vla_engine* e, const uint8_t* images, const int64_t* ext
  * vla_finalize. */
 int vla_set_image_norm(vla_engine* e, const float* mean, const float* stdv);
 
+/* Per-subsystem timing of the forward, for bench.py: with vla_segment_timing(e, 1) the next calls run eagerly (no
+ * graph replay) with CUDA events at the subsystem boundaries; vla_segment_times returns the device time [ms] of the
+ * last call's (0) vision towers + projector, (1) LLM input assembly + Qwen2.5 prefill, (2) Bridge-Attention policy. */
+int vla_segment_timing(vla_engine* e, int enable);
+int vla_segment_times(vla_engine* e, float* ms3);
+
 /* Debug taps for parity tests: copies an intermediate of the LAST vla_predict call to `dst`
  * (device or host).  Names: "patches" (B,NP,2176) tower output, "projected" (B,NP,896),
  * "llm_in" (B,S,896), "hidden.<i>" i in 1..24 (B,S,896) as returned by HF output_hidden_states,

@@ -47,6 +47,8 @@ SIGNATURES = {
     "vla_predict_host_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
     "vla_set_image_norm": (c_int, [c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "vla_segment_timing": (c_int, [c_void_p, c_int]),
+    "vla_segment_times": (c_int, [c_void_p, C.POINTER(C.c_float)]),
     "vla_get_tap": (c_int, [c_void_p, C.c_char_p, c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "vla_last_launch_count": (c_ll, [c_void_p]),
     "vla_last_error": (C.c_char_p, [c_void_p]),

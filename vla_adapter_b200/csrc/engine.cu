@@ -159,6 +159,9 @@ struct vla_engine {
   cudaStream_t gstream = nullptr;
   cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   int use_graphs = 1;
+  // segment timing (vla_segment_times): events at the subsystem boundaries of the last EAGER forward
+  int seg_on = 0;
+  cudaEvent_t seg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
   int fail(int code, const std::string& m) {
     err = m;
@@ -376,6 +379,8 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
   const int M = B * S;
   const int NL = e->cfg.llm_layers;
 
+  const bool seg = e->seg_on && e->seg_ev[0] && s != e->gstream;
+  if (seg) cudaEventRecord(e->seg_ev[0], s);
   // Small batches leave most SMs idle inside every kernel: independent work goes to a side stream (the fork / join
   // are events, so inside a captured CUDA graph they become parallel branches).
   const bool small = e->small_B > 0 && B <= e->small_B;
@@ -411,6 +416,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     CK(vla::gemm_launch(g, s, &_err));
   }
 
+  if (seg) cudaEventRecord(e->seg_ev[1], s);
   // ---------------- LLM input assembly + prefill (MP:418-454, 500-502, 834-845)
   CK(vla::assemble_launch(e->hid[0], B, S, NP, Lext, D_LLM, ext_ids, aq_index, e->embed, e->cfg.vocab_size,
                           e->aq_table, N_AQ, e->err_flag, s, &_err));
@@ -451,6 +457,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     if (rc) return rc;
   }
 
+  if (seg) cudaEventRecord(e->seg_ev[2], s);
   // ---------------- Bridge-Attention policy (AH:43-81, 111-121, 218-283 / 337-410)
   CK(vla::skinny_linear_launch(proprio, 1, P, B, P, e->pp_w1, P, D_LLM, e->pp_b1, 1, e->h_p1, D_LLM, nullptr, s, &_err));
   CK(vla::skinny_linear_launch(e->h_p1, 0, D_LLM, B, D_LLM, e->pp_w2, D_LLM, D_LLM, e->pp_b2, 0, e->h_p, D_LLM, nullptr, s, &_err));
@@ -503,6 +510,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
   }
   CK(vla::head_out_launch(e->head_x[NB], B * T, e->head_ln2w, e->head_ln2b, e->head_fc2_w, e->head_fc2_b, A,
                           e->st_hi, e->st_lo, e->st_mask, out_norm, out_unnorm, s, &_err));
+  if (seg) cudaEventRecord(e->seg_ev[3], s);
   if (out_last_ha)
     CK(vla::gather_rows_launch(e->hid[NL], static_cast<long long>(S) * D_LLM, D_LLM, ha_row0, N_AQ, B, D_LLM,
                                out_last_ha, s, &_err));
@@ -816,7 +824,7 @@ static int predict_impl(vla_engine* e, const void* pixel_values, int is_u8, cons
   bf16* ha = static_cast<bf16*>(out_last_ha);
   int rc = 0;
   vla_engine::GraphEntry* ge = nullptr;
-  if (e->use_graphs && !vla::gemm_profile_enabled()) {
+  if (e->use_graphs && !vla::gemm_profile_enabled() && !e->seg_on) {
     const vla_engine::GraphKey key{B, L, is_u8, pixel_values, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha};
     for (auto& g : e->graphs)
       if (g.key == key) ge = &g;
@@ -1016,6 +1024,25 @@ int vla_get_tap(vla_engine* e, const char* name, void* dst, size_t capacity, siz
   return VLA_OK;
 }
 
+int vla_segment_timing(vla_engine* e, int enable) {
+  if (!e) return VLA_ERR_INVALID;
+  if (enable && !e->seg_ev[0])
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventCreate(&e->seg_ev[i]) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "segment event creation failed");
+  e->seg_on = enable ? 1 : 0;
+  return VLA_OK;
+}
+
+int vla_segment_times(vla_engine* e, float* ms3) {
+  if (!e) return VLA_ERR_INVALID;
+  if (!ms3 || !e->seg_ev[0]) return e->fail(VLA_ERR_INVALID, "segment_times: timing was never enabled");
+  if (cudaEventSynchronize(e->seg_ev[3]) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "segment_times: no timed forward yet");
+  for (int i = 0; i < 3; ++i)
+    if (cudaEventElapsedTime(&ms3[i], e->seg_ev[i], e->seg_ev[i + 1]) != cudaSuccess)
+      return e->fail(VLA_ERR_CUDA, "segment_times: events not recorded");
+  return VLA_OK;
+}
+
 long long vla_last_launch_count(const vla_engine* e) { return e ? e->last_launches : 0; }
 
 const char* vla_last_error(const vla_engine* e) { return e ? e->err.c_str() : "null engine"; }
@@ -1027,6 +1054,8 @@ void vla_destroy(vla_engine* e) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (e->gev_in) cudaEventDestroy(e->gev_in);
   if (e->gev_out) cudaEventDestroy(e->gev_out);
+  for (int i = 0; i < 4; ++i)
+    if (e->seg_ev[i]) cudaEventDestroy(e->seg_ev[i]);
   if (e->gstream) cudaStreamDestroy(e->gstream);
   for (cudaEvent_t ev : e->ev_layer) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->ev_kv) cudaEventDestroy(ev);

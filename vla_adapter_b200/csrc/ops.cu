@@ -45,12 +45,15 @@ norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long lon
   // The row stays packed (bf16) in registers - 4 registers per 16-byte vector instead of 8 floats - so that the
   // kernel fits 2048 threads per SM and keeps enough loads in flight to approach the HBM roofline.
   uint4 u[MAX_VEC_PER_LANE];
-  float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) u[i] = *reinterpret_cast<const uint4*>(xr + vi * 8);
   }
+  // One pass, one round of shuffles: RMSNorm needs sum x^2; LayerNorm takes mean and variance from the sums of
+  // (x - p) and (x - p)^2 around a pivot p (the row's first element), which stays well conditioned when |mean| >> std.
+  const float pivot = RMS ? 0.f : __shfl_sync(0xffffffffu, unpack_bf16(u[0].x).x, 0);
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
     const int vi = lane + i * 32;
@@ -59,32 +62,24 @@ norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long lon
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 a = unpack_bf16(w4[j]);
-        sum += RMS ? a.x * a.x + a.y * a.y : a.x + a.y;
+        const float d0 = a.x - pivot, d1 = a.y - pivot;
+        if (!RMS) s1 += d0 + d1;
+        s2 += d0 * d0 + d1 * d1;
       }
     }
   }
-  sum = warp_sum(sum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    if (!RMS) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
   float mean = 0.f, rstd;
   if (RMS) {
-    rstd = rsqrtf(sum / dim + eps);
+    rstd = rsqrtf(s2 / dim + eps);
   } else {
-    mean = sum / dim;
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        const uint32_t w4[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = unpack_bf16(w4[j]);
-          const float d0 = a.x - mean, d1 = a.y - mean;
-          var += d0 * d0 + d1 * d1;
-        }
-      }
-    }
-    var = warp_sum(var);
-    rstd = rsqrtf(var / dim + eps);
+    const float m1 = s1 / dim;
+    mean = pivot + m1;
+    rstd = rsqrtf(fmaxf(s2 / dim - m1 * m1, 0.f) + eps);
   }
 #pragma unroll
   for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
