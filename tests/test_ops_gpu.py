@@ -68,7 +68,10 @@ def test_gemm_epilogue(act):
     # in-place residual (C aliases resid)
     x = resid.clone()
     ops.linear(a, w, bias=bias, act=act, colscale=ls, resid=x, out=x)
-    assert torch.equal(x, out)
+    # in place the epilogue rounds to bf16 and then TMA-reduce-adds into C (two roundings, like the reference's bf16
+    # `x + y`); out of place it adds the residual in fp32 before the single rounding: equal up to one bf16 ulp
+    assert _rel(x, ref) < 5e-3
+    assert (x.float() - out.float()).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
 
 
 def test_gemm_swiglu():

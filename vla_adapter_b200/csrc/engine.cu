@@ -101,6 +101,9 @@ struct vla_engine {
   // head
   std::vector<HeadBlock> head;
   bf16 *x0, *head_fc2_w, *pp_w1, *pp_w2;
+  bf16* wkv_cond_all = nullptr;   // [24 * 1792, 896]: every block's K|V projection of the cond rows, for the proprio row
+  float* bkv_cond_all = nullptr;  // [24 * 1792]
+  bf16* h_pkv = nullptr;          // [B, 24 * 1792]: K|V of the proprio row for all 24 blocks (one GEMM per forward)
   float *head_ln2w, *head_ln2b, *head_fc2_b, *pp_b1, *pp_b2;
   float *prope_cos = nullptr, *prope_sin = nullptr;
   bf16* img_lut = nullptr;  // [2 towers][3 channels][256]: ToTensor + Normalize + bf16 of a uint8 pixel
@@ -462,6 +465,12 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
   CK(vla::skinny_linear_launch(proprio, 1, P, B, P, e->pp_w1, P, D_LLM, e->pp_b1, 1, e->h_p1, D_LLM, nullptr, s, &_err));
   CK(vla::skinny_linear_launch(e->h_p1, 0, D_LLM, B, D_LLM, e->pp_w2, D_LLM, D_LLM, e->pp_b2, 0, e->h_p, D_LLM, nullptr, s, &_err));
   const int NB = static_cast<int>(e->head.size());
+  {
+    vla::GemmArgs g;  // K|V of the proprio row for all 24 blocks at once
+    g.A = e->h_p; g.lda = D_LLM; g.rows = B; g.W = e->wkv_cond_all; g.ldw = D_LLM; g.N = 24 * PKV; g.K = D_LLM;
+    g.C = e->h_pkv; g.ldc = 24 * PKV; g.bias = e->bkv_cond_all;
+    CK(vla::gemm_launch(g, s, &_err));
+  }
   CK(vla::broadcast_row_launch(e->x0, D_LLM, B * T, e->head_x[0], s, &_err));
   const int ha_row0 = NP + L - 1;  // MP:855 with NUM_PROMPT_TOKENS = L-1 (MP:927)
   const int NK = T + N_AQ + 1 + NP;  // keys per sample: self | h_a ++ p | h_t
@@ -479,12 +488,9 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
       rc = policy_kv_gemms(e, i, hs, B, L, kvb, s);
       if (rc) return rc;
     }
-    // K|V of the proprio row -> kv row T+64
-    g = vla::GemmArgs();
-    g.A = e->h_p; g.a_batch_stride = D_LLM; g.lda = D_LLM; g.rows = 1; g.batches = B;
-    g.W = w.wkv_cond; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
-    g.C = kvb + static_cast<long long>(T + N_AQ) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_cond;
-    CK(vla::gemm_launch(g, s, &_err));
+    // K|V of the proprio row -> kv row T+64 (projected up front for all blocks: one row copy per sample here)
+    CK(vla::copy_view_launch(e->h_pkv + static_cast<long long>(i) * PKV, 24LL * PKV, PKV,
+                             kvb + static_cast<long long>(T + N_AQ) * PKV, kv_bs, PKV, 1, B, PKV, s, &_err));
     // q and self K|V of the current x -> kv rows [0, T)
     g = vla::GemmArgs();
     g.A = e->head_x[i]; g.lda = D_LLM; g.rows = B * T; g.W = w.wq; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
@@ -717,6 +723,16 @@ int vla_finalize(vla_engine* e) {
       }
       e->head.push_back(w);
     }
+    {  // the proprio row is the same for all 24 blocks: its K|V projections become ONE GEMM against the stacked weights
+      e->wkv_cond_all = e->dalloc<bf16>(static_cast<size_t>(24) * PKV * D_LLM);
+      e->bkv_cond_all = e->dalloc<float>(static_cast<size_t>(24) * PKV);
+      for (int i = 0; i < 24; ++i) {
+        cudaMemcpy(e->wkv_cond_all + static_cast<size_t>(i) * PKV * D_LLM, e->head[i].wkv_cond,
+                   static_cast<size_t>(PKV) * D_LLM * sizeof(bf16), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(e->bkv_cond_all + static_cast<size_t>(i) * PKV, e->head[i].bkv_cond, PKV * sizeof(float),
+                   cudaMemcpyDeviceToDevice);
+      }
+    }
     e->head_ln2w = e->f32(hm + "layer_norm2.weight", D_LLM);
     e->head_ln2b = e->f32(hm + "layer_norm2.bias", D_LLM);
     e->head_fc2_w = e->pack(hm + "fc2.weight", e->A, D_LLM);
@@ -782,6 +798,7 @@ int vla_finalize(vla_engine* e) {
         e->ev_kv.push_back(b);
       }
     }
+    e->h_pkv = e->dalloc<bf16>(static_cast<size_t>(B) * 24 * PKV);
     e->h_q = e->dalloc<bf16>(BT * D_LLM);
     e->h_ao = e->dalloc<bf16>(BT * D_LLM);
     e->h_y = e->dalloc<bf16>(BT * D_LLM);

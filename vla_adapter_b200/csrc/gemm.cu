@@ -48,6 +48,10 @@ struct GemmDev {
   const float* colscale;
   int act;
   int accumulate;  // 1: C += epi(...) through TMA reduce-add (C holds the residual)
+  // residual that lives in a DIFFERENT buffer than C: read by the epilogue and added in fp32 (no pre-copy kernel)
+  const __nv_bfloat16* resid;
+  long long r_bs;
+  int ldr;
 };
 
 VLA_DEVINL void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
@@ -312,6 +316,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 f[2 * q + 1] = __fmul2_rn(f[2 * q + 1], make_float2(sv.z, sv.w));
               }
             }
+            if (p.resid) {  // out-of-place residual: this thread's row, 32 columns = four 16-byte loads
+              const int rr = r0 + lane;
+              if (rr < p.rows) {
+                const __nv_bfloat16* rp = p.resid + b * p.r_bs + static_cast<long long>(rr) * p.ldr + c0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (c0 + q * 8 < p.N) {
+                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + q * 8));
+                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) f[4 * q + t] = __fadd2_rn(f[4 * q + t], unpack_bf16(rw[t]));
+                  }
+                }
+              }
+            }
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = pack_bf16(f[j].x, f[j].y);
@@ -426,6 +445,25 @@ int num_sms() {
 
 long long gemm_launch_count() { return g_launches.load(); }
 
+int copy_view_launch(const __nv_bfloat16* src, long long s_bs, int lds, __nv_bfloat16* dst, long long d_bs, int ldd,
+                     int rows, int batches, int cols, cudaStream_t stream, const char** err) {
+  if ((cols & 7) || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15) || (lds & 7) ||
+      (ldd & 7) || (s_bs & 7) || (d_bs & 7)) {
+    if (err) *err = "copy_view: 16-byte alignment required";
+    return -1;
+  }
+  const long long total = static_cast<long long>(batches) * rows * (cols >> 3);
+  launch_kernel(copy_view_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, src, s_bs, lds,
+                dst, d_bs, ldd, rows, batches, cols);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = cudaGetErrorString(e);
+    return -4;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 bool gemm_profile_enabled() { return g_prof_on; }
 
 void gemm_profile_enable(bool on) {
@@ -523,12 +561,18 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   if (swiglu && (bn & 127)) bn = 128;
 
   // Residual: the epilogue adds into C with a TMA reduce-add, so C must hold the residual first.
-  const bool accumulate = a.resid != nullptr;
-  if (accumulate && !(a.resid == a.C && a.ldr == a.ldc && (a.batches == 1 || a.r_batch_stride == a.c_batch_stride))) {
+  // Residual: in place (resid aliases C) the epilogue adds into C with a TMA reduce-add; out of place it reads the
+  // residual rows itself and adds in fp32 before the bf16 store.  (A broadcast residual - batch stride 0, the ViT
+  // position embedding - is pre-copied: its rows are shared by every batch.)
+  const bool in_place = a.resid && a.resid == a.C && a.ldr == a.ldc && (a.batches == 1 || a.r_batch_stride == a.c_batch_stride);
+  const bool fused_resid = a.resid && !in_place && (a.batches == 1 || a.r_batch_stride != 0);
+  bool accumulate = in_place;
+  if (a.resid && !in_place && !fused_resid) {
     const long long total = static_cast<long long>(a.batches) * a.rows * (a.N >> 3);
     launch_kernel(copy_view_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 
         a.resid, a.r_batch_stride, a.ldr, a.C, a.c_batch_stride, a.ldc, a.rows, a.batches, a.N);
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    accumulate = true;
   }
 
   GemmDev p;
@@ -547,6 +591,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.colscale = a.colscale;
   p.act = a.act;
   p.accumulate = accumulate ? 1 : 0;
+  p.resid = fused_resid ? a.resid : nullptr;
+  p.r_bs = a.batches > 1 ? a.r_batch_stride : 0;
+  p.ldr = a.ldr;
 
   CUtensorMap mA, mB, mC;
   const uint64_t a_bs = a.batches > 1 ? static_cast<uint64_t>(a.a_batch_stride)

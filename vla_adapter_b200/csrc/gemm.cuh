@@ -43,6 +43,10 @@ struct GemmArgs {
 // Returns 0 on success, negative on error (message in *err if non-null).
 int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err);
 
+// dst view = src view: `rows` x `cols` bf16 per batch, 16-byte vectors; the source batch stride may be 0.
+int copy_view_launch(const __nv_bfloat16* src, long long s_bs, int lds, __nv_bfloat16* dst, long long d_bs, int ldd,
+                     int rows, int batches, int cols, cudaStream_t stream, const char** err);
+
 // Number of GEMM kernel launches issued since process start (for bench.py's gpu_launches).
 long long gemm_launch_count();
 
