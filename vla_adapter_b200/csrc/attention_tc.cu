@@ -399,7 +399,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       for (int x = 0; x < 2; ++x) {
         if (!it.n[x]) continue;
         const int qb = x * 2 + static_cast<int>(q_cnt[x] & 1u);
-        mbar_wait(q_empty(qb), ((q_cnt[x] >> 1) & 1u) ^ 1u);
+        mbar_wait_relaxed(q_empty(qb), ((q_cnt[x] >> 1) & 1u) ^ 1u);
         ++q_cnt[x];
         if (elect_one()) {
           mbar_arrive_expect_tx(q_full(qb), L::Q_BYTES);
@@ -413,7 +413,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const int s = static_cast<int>(kv_cnt % NS);
         const uint32_t ph = (kv_cnt / NS) & 1u;
         ++kv_cnt;
-        mbar_wait(kv_empty(s), ph ^ 1u);
+        mbar_wait_relaxed(kv_empty(s), ph ^ 1u);
         if (elect_one()) {
           fa_trace(p, 0, tr_cnt, 100 + j);
           mbar_arrive_expect_tx(kv_full(s), L::KV_BYTES);
@@ -655,7 +655,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         named_bar_sync(bar_id, 64);
         l_tot = l + *xo;
       }
-      mbar_wait(o_full(x), o_cnt & 1u);
+      mbar_wait_relaxed(o_full(x), o_cnt & 1u);
       ++o_cnt;
       tc_fence_after();
       if (quarter == 0 && half == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 600 + x);

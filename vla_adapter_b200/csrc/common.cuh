@@ -124,6 +124,14 @@ VLA_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Latency-tolerant wait (e.g. epilogue warps waiting a whole mainloop for their accumulator): back off between polls
+// so the idle warps do not burn issue slots - and power, which is what caps the clocks in this workload.
+VLA_DEVINL void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(100);
+}
+VLA_DEVINL void mbar_wait_short(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(20);
+}
 
 // ---------------------------------------------------------------- TMA
 VLA_DEVINL void tma_prefetch_desc(const CUtensorMap* m) {

@@ -167,7 +167,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       const int r0 = (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM;
       const int n0 = n_idx * p.bn + static_cast<int>(crank) * (p.bn / CG);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);  // the ring is deep: the producer mostly waits, politely
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * stage_bytes;
           if (CG == 2) {
@@ -250,7 +250,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       const int r0 = (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM + quarter * 32;
       const int n0 = n_idx * p.bn + half * wcols;
 
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait_relaxed(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * 256 + half * wcols);
