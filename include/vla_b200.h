@@ -171,6 +171,12 @@ int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_of
                      int n_heads, int group, int hd, int causal, void* out, int ld_out,
                      void* stream);
 
+/* General form: q rows [b*Sq, (b+1)*Sq) of `q` (head h at column h*hd), k / v rows [b*Skv, (b+1)*Skv) of `k` / `v`
+ * (kv head h/group at column (h/group)*hd); hd in {64, 72, 112}.  With Sq = chunk_len, Skv = chunk_len + 65 + 256n,
+ * hd = 112 this is the Bridge-Attention core of MLPResNetBlock (prismatic/models/action_heads.py:256-279). */
+int vla_op_cross_attention(const void* q, int ld_q, int Sq, const void* k, const void* v, int ld_kv, int Skv, int B,
+                           int n_heads, int group, int hd, int causal, void* out, int ld_out, void* stream);
+
 /* Attention kernel selection for vla_op_attention and the engine: 0 = auto (tcgen05/TMEM/TMA kernel for head
  * dims 64 and 72, the small mma.sync kernel for the policy's 8-query hd-112 cross-attention), 1 = mma.sync
  * kernel everywhere (A/B comparison), 2 = tcgen05 kernel whenever the head dim allows.  Returns 0. */

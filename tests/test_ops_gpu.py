@@ -172,6 +172,34 @@ def test_attention(B, S, H, HKV, hd, causal, impl):
     assert _rel(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,Sq,Skv,H,HKV,hd", [
+    (3, 8, 585, 8, 8, 112),     # Bridge-Attention, LIBERO: 8 queries x (8 + 65 + 512) keys
+    (2, 25, 602, 8, 8, 112),    # larger chunk: two 16-row query tiles
+    (2, 8, 329, 8, 8, 112),     # one image: 8 + 65 + 256 keys
+    (1, 5, 261, 14, 2, 64),     # GQA, ragged key split across the four warps
+    (2, 8, 130, 8, 8, 112),     # barely enough keys: the last warps get none
+])
+@pytest.mark.parametrize("impl", [1, 0])   # 1 = generic mma.sync kernel, 0 = split-KV kernel
+def test_cross_attention_few_queries(B, Sq, Skv, H, HKV, hd, impl):
+    from vla_adapter_b200 import ops
+
+    q = _randn(B * Sq, H * hd, seed=31)
+    kv = _randn(B * Skv, 2 * HKV * hd, seed=32)
+    ops.set_attention_impl(impl)
+    try:
+        out = ops.cross_attention(q, kv, B, Sq, Skv, H, HKV, hd)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_attention_impl(0)
+    qf = q.float().view(B, Sq, H, hd).transpose(1, 2)
+    kf = kv[:, :HKV * hd].float().view(B, Skv, HKV, hd).transpose(1, 2).repeat_interleave(H // HKV, dim=1)
+    vf = kv[:, HKV * hd:].float().view(B, Skv, HKV, hd).transpose(1, 2).repeat_interleave(H // HKV, dim=1)
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) / math.sqrt(hd), dim=-1) @ vf).transpose(1, 2).reshape(B * Sq, H * hd)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 2e-2
+    assert _rel(out, ref) < 1e-2
+
+
 def test_attention_large_scores_rescale():
     """Scores that grow by far more than 2^8 from one key tile to the next exercise the lazy O rescale of the
     tcgen05 kernel; the softmax is then nearly one-hot and must still match the fp32 reference."""

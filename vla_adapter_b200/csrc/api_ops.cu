@@ -83,6 +83,15 @@ int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_of
   return rc ? fail(rc, err) : 0;
 }
 
+int vla_op_cross_attention(const void* q, int ld_q, int Sq, const void* k, const void* v, int ld_kv, int Skv, int B,
+                           int n_heads, int group, int hd, int causal, void* out, int ld_out, void* stream) {
+  const char* err = nullptr;
+  int rc = vla::cross_attention_launch(static_cast<const __nv_bfloat16*>(q), ld_q, Sq, static_cast<const __nv_bfloat16*>(k),
+                                       static_cast<const __nv_bfloat16*>(v), ld_kv, Skv, B, n_heads, group, hd, causal,
+                                       static_cast<__nv_bfloat16*>(out), ld_out, static_cast<cudaStream_t>(stream), &err);
+  return rc ? fail(rc, err) : 0;
+}
+
 int vla_set_attention_impl(int impl) {
   vla::attention_set_impl(impl);
   return 0;

@@ -382,7 +382,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
   const int M = B * S;
   const int NL = e->cfg.llm_layers;
 
-  const bool seg = e->seg_on && e->seg_ev[0] && s != e->gstream;
+  const bool seg = e->seg_on && e->seg_ev[0];  // graph capture is off while segment timing is on
   if (seg) cudaEventRecord(e->seg_ev[0], s);
   // Small batches leave most SMs idle inside every kernel: independent work goes to a side stream (the fork / join
   // are events, so inside a captured CUDA graph they become parallel branches).

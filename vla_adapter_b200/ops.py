@@ -87,6 +87,17 @@ def attention(qkv, B, S, n_heads, n_kv_heads, hd, causal):
     return out
 
 
+def cross_attention(q, kv, B, Sq, Skv, n_heads, n_kv_heads, hd):
+    """q: (B*Sq, n_heads*hd); kv: (B*Skv, 2*n_kv_heads*hd) packed [k | v]; non-causal."""
+    _need_cuda(q, kv)
+    out = torch.empty((B * Sq, n_heads * hd), dtype=torch.bfloat16, device=q.device)
+    k, v = kv, kv[:, n_kv_heads * hd:]
+    _lib.check(_lib.load().vla_op_cross_attention(_ptr(q), q.stride(0), Sq, _ptr(k), v.data_ptr(), kv.stride(0), Skv, B,
+                                                   n_heads, n_heads // n_kv_heads, hd, 0, _ptr(out), out.stride(0),
+                                                   _stream()))
+    return out
+
+
 def set_attention_impl(impl: int) -> None:
     """0 = auto, 1 = mma.sync kernel only, 2 = tcgen05 kernel whenever the head dim allows."""
     _lib.check(_lib.load().vla_set_attention_impl(int(impl)))
