@@ -41,7 +41,6 @@ namespace vla {
 namespace {
 
 constexpr int FA_BM = 128;
-constexpr int FA_THREADS = 640;  // warpgroup 0: TMA + MMA warps (+2 idle); warpgroups 1-2: softmax of slot A, 3-4: slot B
 constexpr uint32_t FA_TILE_BYTES = 128 * 128;  // Q tile: 128 rows x 64 bf16
 constexpr uint32_t FA_TAIL_BYTES = 128 * 32;   // Q tail: 128 rows x 16 bf16
 constexpr int FA_MAX_ITEMS = 24;               // work items per (sample, kv head)
@@ -180,7 +179,7 @@ VLA_DEVINL void named_bar_sync(int id, int nthreads) {
 // partner warp of the same TMEM lane quarter owns the other 64 keys).  Scores from TMEM, mask, row max exchanged
 // with the partner through shared memory, running max with lazy O rescale, exp2, partial row sum, P (bf16) back
 // over the score columns.
-template <int HD, int NLIVE, bool MASKED>
+template <int HD, int NLIVE, bool MASKED, bool SPLIT>
 VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint32_t tO, int k0h, int grow, int j, int half,
                                 float sl2, float& m_ref, float& l, float* xch_mine, const float* xch_other, int bar_id,
                                 uint32_t turn_wait, uint32_t turn_parity, uint32_t turn_arrive, uint32_t s_free_bar,
@@ -220,9 +219,12 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
     mloc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   }
   // row max over the whole tile: one float per row each way, one 64-thread named barrier
-  *xch_mine = mloc;
-  named_bar_sync(bar_id, 64);
-  const float m_new = fmaxf(m_ref, fmaxf(mloc, *xch_other));
+  float m_new = fmaxf(m_ref, mloc);
+  if (SPLIT) {
+    *xch_mine = mloc;
+    named_bar_sync(bar_id, 64);
+    m_new = fmaxf(m_new, *xch_other);
+  }
   if (pv_done_bar) {  // PV of the previous tile has retired: O is stable and the P columns may be rewritten
     mbar_wait(pv_done_bar, pv_parity);
     tc_fence_after();
@@ -240,7 +242,7 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
       // s_full(j) was committed after PV(j-1), so O is stable here and PV(j) has not been issued yet.
       constexpr int G = (HD + 7) / 8;
 #pragma unroll 1
-      for (int c = half ? G / 2 : 0; c < (half ? G : G / 2); ++c) {
+      for (int c = (SPLIT && half) ? G / 2 : 0; c < ((SPLIT && !half) ? G / 2 : G); ++c) {
         uint32_t o[8];
         tmem_ld_32x32b_x8(tO + c * 8, o);
         tmem_ld_wait();
@@ -287,7 +289,14 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
 template <int HD, int BN>
 struct FaSmem {
   static constexpr bool TAIL = HD > 64;
-  static constexpr int CTAS_PER_SM = 1;
+  // BN = 128: one CTA per SM, 8 softmax warps per slot (two per TMEM lane quarter split the 128 keys).
+  // BN = 64 : two CTAs per SM (four slots, four independent QK -> softmax -> PV chains per SM), 4 softmax warps
+  //           per slot, 256 TMEM columns per CTA with P aliased over S.
+  static constexpr bool SPLIT = BN == 128;
+  static constexpr int CTAS_PER_SM = SPLIT ? 1 : 2;
+  static constexpr int SM_WARPS = SPLIT ? 8 : 4;             // softmax warps per slot
+  static constexpr int THREADS = 128 + 2 * SM_WARPS * 32;   // warpgroup 0 (TMA, MMA, 2 idle warps) + softmax warps
+  static constexpr int SM_THREADS = SM_WARPS * 32;
   static constexpr int STAGES = 3;
   static constexpr int QBUFS = 4;  // 2 slots x 2 buffers: the next item's Q tiles land while this item computes
   static constexpr uint32_t KV_TILE = BN * 128;  // BN keys x 64 bf16
@@ -303,22 +312,22 @@ struct FaSmem {
   static constexpr uint32_t OFF_VT = OFF_KT + STAGES * KV_TAIL;
   static constexpr uint32_t OFF_BAR = TAIL ? OFF_VT + STAGES * KV_TAIL : OFF_QT;
   static constexpr uint32_t OFF_XCH = OFF_BAR + 256;  // row-max / row-sum exchange: [slot][parity][half][128] floats
-  static constexpr uint32_t TOTAL = OFF_XCH + 2 * 2 * 2 * 128 * 4;  // the dynamic array is __align__(1024): no slack
+  static constexpr uint32_t TOTAL = OFF_XCH + (SPLIT ? 2 * 2 * 2 * 128 * 4 : 0);  // dynamic array is __align__(1024)
   // TMEM columns: S_A [0,BN), S_B [BN,2BN) (P aliases the first half of S), then O_A, O_B
   // Head dim 64 has room for P OUTSIDE the score columns (S_A S_B | P_A P_B | O_A O_B = 256 + 128 + 128): the next
   // tile's QK^T is issued as soon as the softmax warps have read the scores, and PV of this tile runs beside the
   // next tile's softmax.  Head dim 72 (2 x 80 accumulator columns) keeps P aliased over S.
-  static constexpr bool DEALIAS = !TAIL;
+  static constexpr bool DEALIAS = !TAIL && SPLIT;
   static constexpr uint32_t P_OFF = DEALIAS ? 2 * BN : 0;           // + P_STRIDE * slot
   static constexpr uint32_t P_STRIDE = DEALIAS ? 64 : BN;
   static constexpr uint32_t O_OFF = DEALIAS ? 2 * BN + 128 : 2 * BN;
   static constexpr uint32_t O_STRIDE = TAIL ? 128 : 64;
-  static constexpr uint32_t TMEM_COLS = 512;
-  static_assert(!(TAIL && BN == 64), "head dim 72 needs 2*64 + 2*80 TMEM columns: use BN = 128");
+  static_assert(SPLIT || !TAIL, "64-key tiles: head dim 64 only (2 x 64 S + 2 x 64 O = 256 TMEM columns)");
+  static constexpr uint32_t TMEM_COLS = SPLIT ? 512 : 256;
 };
 
 template <int HD, int BN>
-__global__ void __launch_bounds__(FA_THREADS, (FaSmem<HD, BN>::CTAS_PER_SM))
+__global__ void __launch_bounds__((FaSmem<HD, BN>::THREADS), (FaSmem<HD, BN>::CTAS_PER_SM))
 fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                   const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapQt,
                   const __grid_constant__ CUtensorMap mapKt, const __grid_constant__ CUtensorMap mapVt,
@@ -360,13 +369,13 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       mbar_init(q_empty(qb), 1);
     }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(turn(x), 8);
-      mbar_init(s_free(x), 256);
+      mbar_init(turn(x), L::SM_WARPS);
+      mbar_init(s_free(x), L::SM_THREADS);
       mbar_init(pv_done(x), 1);
       mbar_init(s_full(x), 1);
-      mbar_init(p_ready(x), 256);
+      mbar_init(p_ready(x), L::SM_THREADS);
       mbar_init(o_full(x), 1);
-      mbar_init(o_empty(x), 256);
+      mbar_init(o_empty(x), L::SM_THREADS);
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(kv_full(s), 1);
@@ -388,7 +397,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   pdl_launch_dependents();
 
   if (warp_idx < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");  // 128*32 + 512*112 == 640*96 (launch allocation)
+  // register budget: SPLIT 128*32 + 512*112 == 640*96, else 128*32 + 256*104 == 384*80 (the launch allocations)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp_idx == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp waits, one lane issues)
     uint32_t kv_cnt = 0, q_cnt[2] = {0, 0};
@@ -547,15 +557,15 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    if (L::SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ------------------------------------------------------------ softmax + epilogue
     // 8 warps per slot: the two warps of one TMEM lane quarter own the same 32 query rows (one thread per row) and
     // split the tile's 128 keys (and later O's columns) in halves - four softmax warps per SM sub-partition keep the
     // MUFU busy where one warp per sub-partition reaches only ~57 % of its rate (scripts/ubench/expmix.cu).
-    static_assert(BN == 128, "the split-column softmax assumes 128-key tiles");
-    const int x = (warp_idx - 4) >> 3;   // slot
+    const int x = (warp_idx - 4) / L::SM_WARPS;   // slot
     const int quarter = warp_idx & 3;    // TMEM lane quarter this warp may touch
-    const int half = ((warp_idx - 4) >> 2) & 1;  // which 64 keys of a tile / which half of O's columns
+    const int half = L::SPLIT ? ((warp_idx - 4) >> 2) & 1 : 0;  // which 64 keys of a tile / which half of O's columns
     const int row = quarter * 32 + lane;
     const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(BN) * x;
     const uint32_t tO = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + L::O_OFF + L::O_STRIDE * x;
@@ -615,13 +625,13 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           const uint32_t d_bar = (L::DEALIAS && j > 0) ? pv_done(x) : 0u, d_par = d_cnt & 1u;
           if (L::DEALIAS && j > 0) ++d_cnt;
           if (my_live == 2) {
-            if (masked) fa_softmax_tile<HD, 2, true>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
-            else fa_softmax_tile<HD, 2, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            if (masked) fa_softmax_tile<HD, 2, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            else fa_softmax_tile<HD, 2, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           } else if (my_live == 1) {
-            if (masked) fa_softmax_tile<HD, 1, true>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
-            else fa_softmax_tile<HD, 1, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            if (masked) fa_softmax_tile<HD, 1, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            else fa_softmax_tile<HD, 1, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           } else {
-            fa_softmax_tile<HD, 0, false>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            fa_softmax_tile<HD, 0, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           }
           if (my_live < my_all) {  // causal chunks above the diagonal: P = 0
             uint32_t z[16];
@@ -647,7 +657,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       }
       // ---- epilogue: O / l -> bf16 -> global; each warp takes its half of the head's columns of its 32 rows
       float l_tot = l;
-      if (warp_active) {  // total row sum = this warp's keys + the partner's
+      if (warp_active && L::SPLIT) {  // total row sum = this warp's keys + the partner's
         float* xm = xch + (x_cnt & 1u) * 256 + half * 128 + row;
         const float* xo = xch + (x_cnt & 1u) * 256 + (half ^ 1) * 128 + row;
         ++x_cnt;
@@ -660,8 +670,8 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       tc_fence_after();
       if (quarter == 0 && half == 0 && lane == 0) fa_trace(p, 2 + x, tr_cnt, 600 + x);
       constexpr int G = (HD + 7) / 8;                  // 8-column groups of the head
-      constexpr int G0 = G / 2;                        // half 0: groups [0, G0), half 1: [G0, G)
-      constexpr int GMAX = G - G0;
+      constexpr int G0 = L::SPLIT ? G / 2 : G;         // half 0: groups [0, G0), half 1: [G0, G)
+      constexpr int GMAX = L::SPLIT ? G - G0 : G;
       uint32_t o[GMAX][8];
       const int g_lo = half ? G0 : 0, g_n = half ? G - G0 : G0;
       if (warp_active) {
@@ -829,7 +839,7 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
     cudaMemsetAsync(p.trace, 0, 32004 * sizeof(unsigned int), s);
   }
   const int grid = std::min(p.n_items, L::CTAS_PER_SM * fa_num_sms());
-  launch_kernel(fa_tcgen05_kernel<HD, BN>, dim3(grid), dim3(FA_THREADS), L::TOTAL, s, mQ, mK, mV, mQt, mKt, mVt, p);
+  launch_kernel(fa_tcgen05_kernel<HD, BN>, dim3(grid), dim3(L::THREADS), L::TOTAL, s, mQ, mK, mV, mQt, mKt, mVt, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = cudaGetErrorString(e);
@@ -860,6 +870,12 @@ int attention_tc_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfl
                         int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal, __nv_bfloat16* out,
                         int ld_out, cudaStream_t s, const char** err) {
   if ((ld_out & 7) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
+  static int bn64 = -1;  // VLA_FA_BN64=1: 64-key tiles, two CTAs per SM (experiment switch)
+  if (bn64 < 0) {
+    const char* e = getenv("VLA_FA_BN64");
+    bn64 = e ? atoi(e) : 0;
+  }
+  if (hd == 64 && bn64) return launch_fa<64, 64>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
   if (hd == 64) return launch_fa<64, 128>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
   if (hd == 72) return launch_fa<72, 128>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
   return 1;
