@@ -171,6 +171,12 @@ int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_of
                      int n_heads, int group, int hd, int causal, void* out, int ld_out,
                      void* stream);
 
+/* C[m, :] = rope(A[m, :] @ W^T + bias): the Qwen2 q/k/v projection with HF rotate_half RoPE fused into the epilogue.
+ * Output columns [0, rope_cols) are heads of width 64 rotated with position m % S; cos_t / sin_t are [S][32] fp32
+ * tables holding bf16 values (angle = pos * theta^(-2j/64)); columns >= rope_cols (the v heads) pass through. */
+int vla_op_gemm_rope(const void* A, int lda, int rows, const void* W, int ldw, int N, int K, void* C, int ldc,
+                     const float* bias, const float* cos_t, const float* sin_t, int rope_cols, int S, void* stream);
+
 /* General form: q rows [b*Sq, (b+1)*Sq) of `q` (head h at column h*hd), k / v rows [b*Skv, (b+1)*Skv) of `k` / `v`
  * (kv head h/group at column (h/group)*hd); hd in {64, 72, 112}.  With Sq = chunk_len, Skv = chunk_len + 65 + 256n,
  * hd = 112 this is the Bridge-Attention core of MLPResNetBlock (prismatic/models/action_heads.py:256-279). */

@@ -220,6 +220,30 @@ def test_attention_large_scores_rescale():
     assert _rel(out, ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("B,S", [(2, 625), (1, 300), (3, 129)])
+def test_gemm_with_fused_rope_equals_gemm_then_rope(B, S):
+    """The Qwen2 q/k/v projection with RoPE in the GEMM epilogue is bit-identical to the plain GEMM followed by the
+    stand-alone RoPE kernel (which test_rope pins against the HF arithmetic)."""
+    from vla_adapter_b200 import ops
+
+    H, HKV, hd, theta, K = 14, 2, 64, 1e6, 896
+    N = (H + 2 * HKV) * hd
+    a = _randn(B * S, K, seed=41)
+    w = _randn(N, K, scale=K ** -0.5, seed=42)
+    bias = torch.randn(N, device="cuda")
+    ref = ops.linear(a, w, bias=bias)
+    ops.rope_(ref, 0, H + HKV, B, S, theta)
+    inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.float64) / hd))
+    ang = (torch.arange(S, dtype=torch.float32)[:, None] * inv.float()[None, :]).double()
+    cos_t = ang.cos().float().to(torch.bfloat16).float().cuda().contiguous()
+    sin_t = ang.sin().float().to(torch.bfloat16).float().cuda().contiguous()
+    out = ops.linear_rope(a, w, bias, cos_t, sin_t, (H + HKV) * hd, S)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, (H + HKV) * hd:], ref[:, (H + HKV) * hd:])      # v heads untouched
+    diff = (out.float() - ref.float()).abs()
+    assert diff.max().item() <= 0.0625 and (diff > 0).float().mean().item() < 1e-3   # table rounding flips only
+
+
 def test_rope():
     from vla_adapter_b200 import ops
 

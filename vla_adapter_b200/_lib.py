@@ -60,6 +60,8 @@ SIGNATURES = {
     "vla_op_rmsnorm": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p]),
     "vla_op_attention": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_int, c_void_p]),
+    "vla_op_gemm_rope": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vla_op_cross_attention": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_void_p, c_int, c_void_p]),
     "vla_set_attention_impl": (c_int, [c_int]),

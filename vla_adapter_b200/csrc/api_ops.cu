@@ -83,6 +83,28 @@ int vla_op_attention(const void* qkv, int ld_qkv, int q_off, int k_off, int v_of
   return rc ? fail(rc, err) : 0;
 }
 
+int vla_op_gemm_rope(const void* A, int lda, int rows, const void* W, int ldw, int N, int K, void* C, int ldc,
+                     const float* bias, const float* cos_t, const float* sin_t, int rope_cols, int S, void* stream) {
+  vla::GemmArgs g;
+  g.A = static_cast<const __nv_bfloat16*>(A);
+  g.lda = lda;
+  g.rows = rows;
+  g.W = static_cast<const __nv_bfloat16*>(W);
+  g.ldw = ldw;
+  g.N = N;
+  g.K = K;
+  g.C = static_cast<__nv_bfloat16*>(C);
+  g.ldc = ldc;
+  g.bias = bias;
+  g.rope_cos = cos_t;
+  g.rope_sin = sin_t;
+  g.rope_cols = rope_cols;
+  g.rope_S = S;
+  const char* err = nullptr;
+  int rc = vla::gemm_launch(g, static_cast<cudaStream_t>(stream), &err);
+  return rc ? fail(rc, err) : 0;
+}
+
 int vla_op_cross_attention(const void* q, int ld_q, int Sq, const void* k, const void* v, int ld_kv, int Skv, int B,
                            int n_heads, int group, int hd, int causal, void* out, int ld_out, void* stream) {
   const char* err = nullptr;

@@ -52,6 +52,9 @@ struct GemmDev {
   const __nv_bfloat16* resid;
   long long r_bs;
   int ldr;
+  const float* rope_cos;  // RoPE fused into the epilogue (see GemmArgs)
+  const float* rope_sin;
+  int rope_cols, rope_S;
 };
 
 VLA_DEVINL void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
@@ -275,6 +278,61 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             }
             store_box(&mapC, buf0 + buf * 2048u, lane, o, c0 >> 1, r0, b, 0);
             buf ^= 1;
+          }
+        } else if (p.rope_cols > 0) {
+          // q/k projection with RoPE: a 64-wide head = two 32-column chunks (lo, hi) of this warp; out_lo = lo*cos -
+          // hi*sin, out_hi = hi*cos + lo*sin, every product and sum rounded to bf16 like the eager reference
+          const int rr = r0 + lane;
+          const int pos = rr % p.rope_S;
+#pragma unroll 1
+          for (int ch = 0; ch < wcols; ch += 64) {
+            const int c0 = n0 + ch;
+            if (c0 >= p.N) break;
+            uint32_t vl[32], vh[32];
+            tmem_ld_32x32b_x32(t_row + ch, vl);
+            tmem_ld_32x32b_x32(t_row + ch + 32, vh);
+            tmem_ld_wait();
+            const bool rot = c0 < p.rope_cols;
+            uint32_t ol[16], oh[16];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 bl = make_float4(0.f, 0.f, 0.f, 0.f), bh = bl;
+              if (p.bias) {
+                if (c0 + q * 4 < p.N) bl = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + q * 4));
+                if (c0 + 32 + q * 4 < p.N) bh = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 32 + q * 4));
+              }
+              const float bls[4] = {bl.x, bl.y, bl.z, bl.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w};
+              float cs[4] = {1.f, 1.f, 1.f, 1.f}, sn[4] = {0.f, 0.f, 0.f, 0.f};
+              if (rot) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.rope_cos + pos * 32 + q * 4));
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.rope_sin + pos * 32 + q * 4));
+                cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
+                sn[0] = s4.x; sn[1] = s4.y; sn[2] = s4.z; sn[3] = s4.w;
+              }
+              float rl[4], rh[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float a = bf16_round(__uint_as_float(vl[4 * q + t]) + bls[t]);   // the projection output, bf16
+                const float bq = bf16_round(__uint_as_float(vh[4 * q + t]) + bhs[t]);
+                if (rot) {
+                  rl[t] = bf16_round(bf16_round(a * cs[t]) + bf16_round(-bq * sn[t]));
+                  rh[t] = bf16_round(bf16_round(bq * cs[t]) + bf16_round(a * sn[t]));
+                } else {
+                  rl[t] = a;
+                  rh[t] = bq;
+                }
+              }
+              ol[2 * q] = pack_bf16(rl[0], rl[1]);
+              ol[2 * q + 1] = pack_bf16(rl[2], rl[3]);
+              oh[2 * q] = pack_bf16(rh[0], rh[1]);
+              oh[2 * q + 1] = pack_bf16(rh[2], rh[3]);
+            }
+            store_box(&mapC, buf0 + buf * 2048u, lane, ol, c0, r0, b, 0);
+            buf ^= 1;
+            if (c0 + 32 < p.N) {
+              store_box(&mapC, buf0 + buf * 2048u, lane, oh, c0 + 32, r0, b, 0);
+              buf ^= 1;
+            }
           }
         } else {
 #pragma unroll 1
@@ -559,6 +617,15 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     }
   }
   if (swiglu && (bn & 127)) bn = 128;
+  const bool rope = a.rope_cols > 0;
+  if (rope) {
+    if (!a.rope_cos || !a.rope_sin || a.rope_S <= 0 || (a.rope_cols & 63) || (a.N & 63) || a.rope_cols > a.N || swiglu ||
+        a.act != ACT_NONE || a.colscale || a.resid || a.batches != 1) {
+      if (err) *err = "gemm: fused RoPE needs plain bias epilogue, one row view, N and rope_cols multiples of 64";
+      return -1;
+    }
+    if (bn != 128 && bn != 256) bn = 128;  // a head (64 columns) must sit inside one epilogue warp's column range
+  }
 
   // Residual: the epilogue adds into C with a TMA reduce-add, so C must hold the residual first.
   // Residual: in place (resid aliases C) the epilogue adds into C with a TMA reduce-add; out of place it reads the
@@ -594,6 +661,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.resid = fused_resid ? a.resid : nullptr;
   p.r_bs = a.batches > 1 ? a.r_batch_stride : 0;
   p.ldr = a.ldr;
+  p.rope_cos = a.rope_cos;
+  p.rope_sin = a.rope_sin;
+  p.rope_cols = rope ? a.rope_cols : 0;
+  p.rope_S = a.rope_S;
 
   CUtensorMap mA, mB, mC;
   const uint64_t a_bs = a.batches > 1 ? static_cast<uint64_t>(a.a_batch_stride)

@@ -38,6 +38,12 @@ struct GemmArgs {
   int ldr = 0;
   int act = ACT_NONE;
   int force_bn = 0;  // 0 = heuristic, else 64/128/256
+  // HF rotate_half RoPE fused into the epilogue (Qwen2 q/k projection): output columns [0, rope_cols) are heads of
+  // width 64 rotated with the cos/sin of position (row % rope_S); tables are [rope_S][32] fp32 holding bf16 values.
+  const float* rope_cos = nullptr;
+  const float* rope_sin = nullptr;
+  int rope_cols = 0;
+  int rope_S = 0;
 };
 
 // Returns 0 on success, negative on error (message in *err if non-null).

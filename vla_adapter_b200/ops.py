@@ -87,6 +87,17 @@ def attention(qkv, B, S, n_heads, n_kv_heads, hd, causal):
     return out
 
 
+def linear_rope(a, w, bias, cos_t, sin_t, rope_cols, S):
+    """out = rope(a @ w.T + bias): q/k/v projection with RoPE fused into the GEMM epilogue (cos_t/sin_t: (S, 32) fp32)."""
+    _need_cuda(a, w, bias, cos_t, sin_t)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _lib.check(_lib.load().vla_op_gemm_rope(_ptr(a), a.stride(0), M, _ptr(w), w.stride(0), N, K, _ptr(out), out.stride(0),
+                                             _ptr(bias), _ptr(cos_t), _ptr(sin_t), rope_cols, S, _stream()))
+    return out
+
+
 def cross_attention(q, kv, B, Sq, Skv, n_heads, n_kv_heads, hd):
     """q: (B*Sq, n_heads*hd); kv: (B*Skv, 2*n_kv_heads*hd) packed [k | v]; non-causal."""
     _need_cuda(q, kv)
