@@ -108,6 +108,25 @@ def test_gemm_batched_view():
     assert out[:, :65].abs().sum().item() == 0 and out[:, 577:].abs().sum().item() == 0
 
 
+@pytest.mark.parametrize("rows,B", [(8, 5), (8, 64), (64, 3), (1, 7), (16, 9), (25, 4), (32, 6)])
+def test_gemm_short_row_views_packed(rows, B):
+    """Short row views (the policy's T rows / 64 ActionQuery rows per sample): 128 / rows samples share one M tile.
+    Rows that divide 128 take the packed path, 25 (the larger-chunk preset) the plain one; nothing outside the view
+    may be written."""
+    from vla_adapter_b200 import ops
+
+    R, R2, K, N = 40, 70, 896, 1792
+    a = _randn(B, R, K, seed=51)
+    w = _randn(N, K, scale=K ** -0.5, seed=52)
+    bias = torch.randn(N, device="cuda")
+    out = torch.zeros(B, R2, N, dtype=torch.bfloat16, device="cuda")
+    rows = min(rows, R - 3)
+    ops.linear_batched(a, 3, rows, w, out, 5, bias=bias)
+    ref = a[:, 3:3 + rows].float() @ w.float().T + bias
+    assert _rel(out[:, 5:5 + rows], ref) < 5e-3
+    assert out[:, :5].abs().sum().item() == 0 and out[:, 5 + rows:].abs().sum().item() == 0
+
+
 @pytest.mark.parametrize("dim", [896, 1024, 1152])
 def test_layernorm(dim):
     from vla_adapter_b200 import ops

@@ -42,6 +42,7 @@ constexpr int MAX_STAGES = 8;
 struct GemmDev {
   int rows, batches, N, K;
   int mt_per_batch, tiles_m, tiles_n;
+  int pack;        // > 0: short row views (rows < 128, 128 % rows == 0): one M tile = `pack` consecutive batches
   int bn;          // tile width: 64 / 128 / 192 / 256
   int stages;      // smem ring depth = min(8, 192 KB / stage bytes)
   const float* bias;
@@ -166,8 +167,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int n_idx = tile % p.tiles_n;
       const int m_idx = tile / p.tiles_n;
-      const int b = m_idx / p.mt_per_batch;
-      const int r0 = (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM;
+      // packed short views: the A box is (64, rows, pack) - `pack` whole batches land as 128 dense smem rows
+      const int b = p.pack ? m_idx * p.pack : m_idx / p.mt_per_batch;
+      const int r0 = p.pack ? 0 : (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM;
       const int n0 = n_idx * p.bn + static_cast<int>(crank) * (p.bn / CG);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);  // the ring is deep: the producer mostly waits, politely
@@ -249,15 +251,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int n_idx = tile % p.tiles_n;
       const int m_idx = tile / p.tiles_n;
-      const int b = m_idx / p.mt_per_batch;
-      const int r0 = (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM + quarter * 32;
+      int b = m_idx / p.mt_per_batch;
+      int r0 = (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM + quarter * 32;
+      if (p.pack) {  // this warp's 32 tile rows = rows [t0 % rows, ...) of batch m_idx*pack + t0 / rows (and the next ones)
+        const int t0 = quarter * 32;
+        b = m_idx * p.pack + t0 / p.rows;
+        r0 = t0 % p.rows;
+      }
+      const bool live = p.pack ? b < p.batches : r0 < p.rows;
       const int n0 = n_idx * p.bn + half * wcols;
 
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * 256 + half * wcols);
-      if (r0 < p.rows && n0 < p.N) {  // warp-uniform: sub-tiles entirely out of bounds are skipped
+      if (live && n0 < p.N) {  // warp-uniform: sub-tiles entirely out of bounds are skipped
         if (swiglu) {
 #pragma unroll 1
           for (int ch = 0; ch < wcols; ch += 64) {
@@ -462,12 +470,12 @@ EncodeTiledFn get_encode_fn() {
 // with 64B swizzle (the epilogue's staging layout).
 bool make_map_3d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t batches,
                  uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_inner, uint32_t box_rows,
-                 CUtensorMapSwizzle swz) {
+                 CUtensorMapSwizzle swz, uint32_t box_batches = 1) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {inner, rows, batches};
   cuuint64_t strides[2] = {row_stride_elems * 2, batch_stride_elems * 2};
-  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t box[3] = {box_inner, box_rows, box_batches};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -596,8 +604,19 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     cg_env = e ? atoi(e) : 0;
   }
   const int cg = cg_env == 1 ? 1 : (cg_env == 2 ? 2 : (a.rows >= 2 * BM ? 2 : 1));
+  // Short row views (the policy's 8 / 64 rows per sample): pack 128 / rows samples into one M tile instead of
+  // spending a 128-row tile on each of them.  VLA_GEMM_PACK=0 switches it off.
+  static int pack_env = -1;
+  if (pack_env < 0) {
+    const char* e = getenv("VLA_GEMM_PACK");
+    pack_env = e ? atoi(e) : 1;
+  }
+  int pack = 0;
+  if (pack_env && cg == 1 && a.batches > 1 && a.rows < BM && (BM % a.rows) == 0 && !a.resid && a.rope_cols == 0 &&
+      !swiglu && (a.rows >= 32 || (32 % a.rows) == 0))
+    pack = BM / a.rows;
   const int mt_per_batch = (a.rows + BM * cg - 1) / (BM * cg);
-  const int tiles_m = mt_per_batch * a.batches;
+  const int tiles_m = pack ? (a.batches + pack - 1) / pack : mt_per_batch * a.batches;
   const int sms = num_sms() / cg;  // scheduling units: CTAs or CTA pairs
   // Tile-width heuristic: fewest (rounds over the SMs) x (tile width + fixed per-tile cost).
   int bn = a.force_bn;
@@ -648,6 +667,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.N = a.N;
   p.K = a.K;
   p.mt_per_batch = mt_per_batch;
+  p.pack = pack;
   p.tiles_m = tiles_m;
   p.tiles_n = (a.N + bn - 1) / bn;
   p.bn = bn;
@@ -672,10 +692,14 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   const uint64_t c_bs = a.batches > 1 ? static_cast<uint64_t>(a.c_batch_stride)
                                       : static_cast<uint64_t>(a.rows) * a.ldc;
   const uint64_t n_out = swiglu ? a.N / 2 : a.N;
-  if (!make_map_3d(&mA, a.A, a.K, a.rows, a.batches, a.lda, a_bs, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B) ||
+  const uint32_t c_box_rows = pack ? static_cast<uint32_t>(a.rows < 32 ? a.rows : 32) : 32u;
+  const uint32_t c_box_batches = pack ? 32u / c_box_rows : 1u;
+  if (!make_map_3d(&mA, a.A, a.K, a.rows, a.batches, a.lda, a_bs, BK, pack ? a.rows : BM, CU_TENSOR_MAP_SWIZZLE_128B,
+                   pack ? pack : 1) ||
       !make_map_3d(&mB, a.W, a.K, a.N, 1, a.ldw, static_cast<uint64_t>(a.N) * a.ldw, BK, bn / cg,
                    CU_TENSOR_MAP_SWIZZLE_128B) ||
-      !make_map_3d(&mC, a.C, n_out, a.rows, a.batches, a.ldc, c_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) {
+      !make_map_3d(&mC, a.C, n_out, a.rows, a.batches, a.ldc, c_bs, 32, c_box_rows, CU_TENSOR_MAP_SWIZZLE_64B,
+                   c_box_batches)) {
     if (err) *err = "gemm: cuTensorMapEncodeTiled failed";
     return -4;
   }
