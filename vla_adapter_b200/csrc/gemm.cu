@@ -628,7 +628,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
       if (swiglu && (c & 127)) continue;  // a SwiGLU output box needs 64 accumulator columns per warp
       const long long tiles = static_cast<long long>(tiles_m) * ((a.N + c - 1) / c);
       const long long rounds = (tiles + sms - 1) / sms;
-      const long long cost = rounds * (c + 96);  // measured: narrow tiles pay ~96 columns of fixed cost
+      // measured fixed cost per tile, in columns: ~96 for single CTAs, ~64 for CTA pairs (sig.fc2 / llm.down then take
+      // 192-wide tiles that divide N = 1152 / 896 better than 256)
+      const long long cost = rounds * (c + (cg == 2 ? 64 : 96));
       if (best < 0 || cost < best) {
         best = cost;
         bn = c;
