@@ -379,7 +379,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(kv_empty(s), 2);  // one release per slot's MMA warp
     }
     mbar_fence_init();
     fence_proxy_async();
@@ -437,14 +437,21 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         __syncwarp();
       }
     }
-  } else if (warp_idx == 1) {
-    // ------------------------------------------------------------ MMA issuer (whole warp waits, one lane issues)
-    uint32_t kv_cnt = 0, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0}, o_cnt[2] = {0, 0}, f_cnt[2] = {0, 0};
+  } else if (warp_idx == 1 || warp_idx == 2) {
+    // ------------------------------------------------------------ MMA issuers: one warp per slot (whole warp waits,
+    // one lane issues).  A single issuer serialises the waits of both slots' QK -> softmax -> PV chains - its
+    // wait / issue / commit loop alone was the pacing stage of the kernel's skeleton.
+    const int x = warp_idx - 1;
+    uint32_t kv_cnt = 0, q_cnt = 0, p_cnt = 0, o_cnt = 0, f_cnt = 0;
     unsigned int tr_cnt = 0;
     const uint32_t idesc_pv = make_idesc_bf16(128, 64) | (1u << 16);
     const uint32_t idesc_pvt = make_idesc_bf16(128, 16) | (1u << 16);
+    const uint32_t tS = tmem_base + static_cast<uint32_t>(BN) * x;
+    const uint32_t tP = tmem_base + L::P_OFF + L::P_STRIDE * x;  // P columns (over S unless de-aliased)
+    const uint32_t tO = tmem_base + L::O_OFF + L::O_STRIDE * x;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const FaItem it = fa_decode(p, item);
+      const int n_x = it.n[x];
       const uint32_t kv0 = kv_cnt;  // ring position of this item's key tile 0
       kv_cnt += static_cast<uint32_t>(it.nmax);
       int kv_waited = 0;            // key tiles [0, kv_waited) of this item are known to have landed
@@ -462,14 +469,13 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         if (nvalid > BN) nvalid = BN;
         return (nvalid + 15) >> 4;  // key columns actually computed, in units of 16
       };
-      int qbuf[2] = {0, 0};
+      int qbuf = 0;
       // S_x = Q_x K_j^T   (M = 128 query rows, N = n16*16 keys, K = head dim)
-      auto issue_qk = [&](int x, int j) {
+      auto issue_qk = [&](int j) {
         need_kv(j);
         const int s = stage_of(j);
-        const uint32_t tS = tmem_base + static_cast<uint32_t>(BN) * x;
         const uint32_t idesc_qk = make_idesc_bf16(128, static_cast<uint32_t>(n16_of(j) * 16));
-        const uint32_t sq = sbase + L::OFF_Q + qbuf[x] * FA_TILE_BYTES, sk = sbase + L::OFF_K + s * L::KV_TILE;
+        const uint32_t sq = sbase + L::OFF_Q + qbuf * FA_TILE_BYTES, sk = sbase + L::OFF_K + s * L::KV_TILE;
         if (elect_one()) {
           if (!(p.debug & 4)) {
 #pragma unroll
@@ -477,82 +483,79 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
               umma_bf16(tS, make_smem_desc(sq + k * 32, 1024, LAYOUT_SW128),
                         make_smem_desc(sk + k * 32, 1024, LAYOUT_SW128), idesc_qk, k != 0 ? 1u : 0u);
             if (TAIL)
-              umma_bf16(tS, make_smem_desc(sbase + L::OFF_QT + qbuf[x] * FA_TAIL_BYTES, 256, LAYOUT_SW32),
+              umma_bf16(tS, make_smem_desc(sbase + L::OFF_QT + qbuf * FA_TAIL_BYTES, 256, LAYOUT_SW32),
                         make_smem_desc(sbase + L::OFF_KT + s * L::KV_TAIL, 256, LAYOUT_SW32), idesc_qk, 1u);
           }
           umma_commit(s_full(x));
-          if (j == it.n[x] - 1) umma_commit(q_empty(qbuf[x]));  // last use of this Q tile
+          if (j == n_x - 1) umma_commit(q_empty(qbuf));  // last use of this Q tile
         }
         __syncwarp();
       };
       // O_x (+)= P_x V_j   (A = P from TMEM, B = V MN-major: K = keys, N = head dim)
-      auto issue_pv = [&](int x, int j) {
+      auto issue_pv = [&](int j) {
         const int s = stage_of(j);
         const int n16 = n16_of(j);
-        const uint32_t tS = tmem_base + L::P_OFF + L::P_STRIDE * x;  // P columns (over S unless de-aliased)
-        const uint32_t tO = tmem_base + L::O_OFF + L::O_STRIDE * x;
         const uint32_t sv = sbase + L::OFF_V + s * L::KV_TILE;
         if (elect_one()) {
           if (!(p.debug & 2)) {
             for (int kk = 0; kk < n16; ++kk)
-              umma_bf16_ts(tO, tS + kk * 8, make_smem_desc(sv + kk * 2048, 1024, LAYOUT_SW128), idesc_pv,
+              umma_bf16_ts(tO, tP + kk * 8, make_smem_desc(sv + kk * 2048, 1024, LAYOUT_SW128), idesc_pv,
                            (j | kk) != 0 ? 1u : 0u);
             if (TAIL) {
               const uint32_t svt = sbase + L::OFF_VT + s * L::KV_TAIL;
               for (int kk = 0; kk < n16; ++kk)
-                umma_bf16_ts(tO + 64, tS + kk * 8, make_smem_desc(svt + kk * 512, 256, LAYOUT_SW32), idesc_pvt,
+                umma_bf16_ts(tO + 64, tP + kk * 8, make_smem_desc(svt + kk * 512, 256, LAYOUT_SW32), idesc_pvt,
                              (j | kk) != 0 ? 1u : 0u);
             }
           }
         }
         __syncwarp();
       };
-#pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        if (!it.n[x]) continue;
-        qbuf[x] = x * 2 + static_cast<int>(q_cnt[x] & 1u);
-        mbar_wait(q_full(qbuf[x]), (q_cnt[x] >> 1) & 1u);
-        ++q_cnt[x];
+      if (n_x) {
+        qbuf = x * 2 + static_cast<int>(q_cnt & 1u);
+        mbar_wait(q_full(qbuf), (q_cnt >> 1) & 1u);
+        ++q_cnt;
         tc_fence_after();
-        issue_qk(x, 0);
+        issue_qk(0);
       }
       for (int j = 0; j < it.nmax; ++j) {
-        if (L::DEALIAS) {
-          // the next tile's scores as soon as this tile's have been read: S(j+1) is ready before softmax(j) ends
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            if (j >= it.n[x]) continue;
-            mbar_wait(s_free(x), f_cnt[x] & 1u);
-            ++f_cnt[x];
+        if (j < n_x) {
+          if (L::DEALIAS) {
+            // the next tile's scores as soon as this tile's have been read: S(j+1) is ready before softmax(j) ends
+            mbar_wait(s_free(x), f_cnt & 1u);
+            ++f_cnt;
             tc_fence_after();
-            if (j + 1 < it.n[x] && !(p.debug & 16)) issue_qk(x, j + 1);
+            if (j + 1 < n_x && !(p.debug & 16)) issue_qk(j + 1);
           }
-        }
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          if (j >= it.n[x]) continue;
-          mbar_wait(p_ready(x), p_cnt[x] & 1u);
+          mbar_wait(p_ready(x), p_cnt & 1u);
           if (lane == 0) fa_trace(p, 1, tr_cnt, 300 + x * 10 + j);
-          ++p_cnt[x];
-          if (j == 0) mbar_wait(o_empty(x), (o_cnt[x] & 1u) ^ 1u);  // previous item's epilogue has drained O_x
+          ++p_cnt;
+          if (j == 0) mbar_wait(o_empty(x), (o_cnt & 1u) ^ 1u);  // previous item's epilogue has drained O_x
           tc_fence_after();
-          issue_pv(x, j);
-          if (j + 1 < it.n[x]) {
+          issue_pv(j);
+          if (j + 1 < n_x) {
             if (L::DEALIAS) {
               if (elect_one()) umma_commit(pv_done(x));  // P_x / O_x may be touched again by the softmax warps
               __syncwarp();
-              if (p.debug & 16) issue_qk(x, j + 1);  // (experiment: no early issue)
+              if (p.debug & 16) issue_qk(j + 1);  // (experiment: no early issue)
             } else {
-              issue_qk(x, j + 1);  // in-order after PV(j): S_x / P_x is free again
+              issue_qk(j + 1);  // in-order after PV(j): S_x / P_x is free again
             }
           } else {
             if (elect_one()) umma_commit(o_full(x));
             __syncwarp();
-            ++o_cnt[x];
+            ++o_cnt;
           }
+          // this slot's MMAs on key tile j have all been issued: its half of the release of the K/V ring slot
+          if (elect_one()) umma_commit(kv_empty(stage_of(j)));
+          __syncwarp();
+        } else {
+          // this slot is idle (or already past its causal extent) for key tile j: release its half right away - but
+          // only once the tile has landed, so the arrival cannot fall into an earlier phase of the same slot
+          need_kv(j);
+          if (elect_one()) mbar_arrive(kv_empty(stage_of(j)));
+          __syncwarp();
         }
-        if (elect_one()) umma_commit(kv_empty(stage_of(j)));  // every MMA that read key tile j has been issued above
-        __syncwarp();
       }
     }
   }
