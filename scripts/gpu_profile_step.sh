@@ -11,7 +11,7 @@ rm -f gpurun_out/gemm_shapes.csv
 VLA_GEMM_PROF_CSV=gpurun_out/gemm_shapes.csv $CMD > gpurun_out/plain.log 2>&1 || { tail -5 gpurun_out/plain.log; exit 1; }
 N=$(python -c "import json;print(json.loads(open('gpurun_out/plain.log').read().strip().splitlines()[-1])['gpu_launches'])")
 echo "launches per step: $N"
-KRE='gemm_bf16|flash_attn|fa_tcgen05|norm_kernel|rope_apply|im2col|prefix_tokens|assemble|skinny|policy_|head_out|broadcast_row|gather_rows|copy_view'
+KRE='gemm_bf16|flash_attn|splitkv_attn|fa_tcgen05|norm_kernel|rope_apply|im2col|prefix_tokens|assemble|skinny|policy_|head_out|broadcast_row|gather_rows|copy_view'
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     -k regex:"$KRE" -s $((3*N)) -c $N --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu.log 2>&1
 echo "launch list rc=$?"
