@@ -6,26 +6,26 @@
 //   SigLIP  : 16 heads x 72, S = 256, bidirectional
 //   Qwen2.5 : 14 q / 2 kv heads x 64, S ~ 625, causal (modeling_prismatic.py:834-845 -> Qwen2Attention)
 //
-// Persistent kernel, one CTA per SM.  A work item is a PAIR of 128-row query tiles ("slots" A and B) that share
-// one K/V stream: two query tiles of one head (ViT) or two query heads of one kv group (Qwen GQA), so every K/V
-// tile is fetched once for 256 query rows.  Roles (384 threads = 3 warpgroups; setmaxnreg moves registers from warpgroup 0 to the softmax warpgroups):
-//   warp 0    : TMA producer - Q tiles of both slots, K/V tiles of 128 keys through an mbarrier ring that runs
-//                              ahead across work items (the next item's operands land while this one computes)
-//   warp 1    : MMA issuer   - per slot S = Q K^T (SS, 128 x keys x hd) into TMEM, then O += P V (TS: P is read
-//                              from TMEM, V is the MN-major smem operand); tcgen05.commit -> mbarriers.  The two
-//                              slots are interleaved so the tensor pipe works on one while the other is in softmax.
-//   warps 4-7 : softmax + epilogue of slot A, warps 8-11 of slot B - one thread per query row: tcgen05.ld the
-//                              fp32 score row, mask, running max with lazy rescaling of O (only when the max grows
-//                              by > 2^8), exp2, row sum, P -> bf16 -> tcgen05.st over the score columns; finally
-//                              O / l -> bf16 -> global.
-// Two configurations: head dim 64 uses 64-key tiles and 256 TMEM columns so that TWO CTAs (four slots) share an SM -
-// each slot's QK -> softmax -> PV chain is latency-bound, four chains keep the MUFU and the tensor pipe busy; head
-// dim 72 needs 2*80 accumulator columns and runs 128-key tiles with one CTA per SM.
-// TMEM columns: S_A [0,BN) (P_A aliases its first half), S_B [BN,2BN), then O_A, O_B.
+// Persistent kernel, one CTA (640 threads) per SM.  A work item is a PAIR of 128-row query tiles ("slots" A and B) that
+// share one K/V stream: two query tiles of one head (ViT) or two query heads of one kv group (Qwen GQA), so every K/V
+// tile is fetched once for 256 query rows.  Roles (setmaxnreg moves registers from warpgroup 0 to the softmax warps):
+//   warp 0      : TMA producer - Q tiles of both slots (double-buffered), K/V tiles of 128 keys through an mbarrier
+//                 ring that runs ahead across work items (the next item's operands land while this one computes)
+//   warps 1, 2  : MMA issuers, one per slot - S = Q K^T (SS, 128 x keys x hd) into TMEM, then O += P V (TS: P is read
+//                 from TMEM, V is the MN-major smem operand exactly as TMA delivers it); tcgen05.commit -> mbarriers
+//   warps 4-11  : softmax + epilogue of slot A, warps 12-19 of slot B.  The two warps of one TMEM lane quarter own
+//                 the same 32 query rows (one thread per row) and split the tile's 128 keys; row max and row sum are
+//                 exchanged through shared memory.  tcgen05.ld the fp32 scores, mask, running max with lazy
+//                 rescaling of O (only when the max grows by > 2^8), exp2 (packed FFMA2 / FADD2), P -> bf16 ->
+//                 tcgen05.st; finally O / l -> bf16 -> global.
+// TMEM columns, head dim 64: S_A S_B | P_A P_B | O_A O_B (P outside the score columns: the next tile's Q K^T is issued
+// as soon as the scores have been read, and P V runs beside the next tile's softmax).  Head dim 72 (2 x 80 accumulator
+// columns) keeps P aliased over S: S_A S_B | O_A O_B.
 //
 // Head dim 72 is handled as a 64-wide main block (128B-swizzled tiles) plus a 16-wide tail block
 // (32B-swizzled tiles) whose columns 72..79 are zero-filled by TMA: the tensor maps are per-head 4-D views
 // (d, head, row, sample) so that out-of-head columns count as out of bounds.
+// An experimental configuration with 64-key tiles and two CTAs per SM is kept behind VLA_FA_BN64=1 (measured a wash).
 #include "common.cuh"
 #include "launch.cuh"
 #include "ops.cuh"
@@ -139,17 +139,6 @@ VLA_DEVINL void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* r) {
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-VLA_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
-      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
-      "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
 VLA_DEVINL void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* r) {
