@@ -165,6 +165,42 @@ def test_engine_error_paths():
     eng.close()
 
 
+def test_engine_limits_and_bad_inputs():
+    """Boundary shapes and the error behaviour of the C ABI: shortest prompt, full max_batch / max_prompt_len, batch
+    or prompt beyond the workspace, token ids outside the vocabulary (device-side check), wrong pixel shape."""
+    from vla_adapter_b200.engine import VLAEngine
+
+    cfg = O.OracleConfig(n_images=1, dino_depth=2, siglip_depth=2, vocab_size=512, pro=False)
+    W = O.make_weights(cfg, seed=9)
+    eng = VLAEngine(n_images=1, dino_depth=2, siglip_depth=2, vocab_size=512, max_batch=3, max_prompt_len=12)
+    eng.load_flat(W)
+    eng.finalize()
+    for B, L in [(1, 1), (3, 12), (2, 5)]:
+        pix, ids, prop = O.make_inputs(cfg, B, L, seed=B * 10 + L)
+        a, n = eng.predict_action_batch(ids, None, pix, prop)
+        ref = O.predict_action_batch(W, cfg, pix, ids, prop, torch.float32)["normalized"].numpy()
+        assert a.shape == (B, 8, 7) and np.isfinite(n).all()
+        assert np.abs(n - ref).max() < 5e-2, (B, L)
+    pix, ids, prop = O.make_inputs(cfg, 4, 8, seed=1)
+    with pytest.raises(ValueError):                      # batch beyond max_batch
+        eng.predict_action_batch(ids, None, pix, prop)
+    pix, ids, prop = O.make_inputs(cfg, 2, 13, seed=1)
+    with pytest.raises(ValueError):                      # prompt beyond max_prompt_len
+        eng.predict_action_batch(ids, None, pix, prop)
+    pix, ids, prop = O.make_inputs(cfg, 2, 6, seed=1)
+    bad = ids.clone()
+    bad[1, 3] = 512                                      # first id outside the vocabulary
+    with pytest.raises(ValueError):
+        eng.predict_action_batch(bad, None, pix, prop)
+    a, n = eng.predict_action_batch(ids, None, pix, prop)   # the engine stays usable after a rejected call
+    assert np.isfinite(n).all()
+    with pytest.raises(ValueError):                      # padded prompts are not part of the path (reference is bs=1)
+        eng.predict_action_batch(ids, torch.tensor([[1] * 6, [1] * 5 + [0]]), pix, prop)
+    with pytest.raises(ValueError):                      # wrong number of image channels
+        eng.predict_action_batch(ids, None, pix[:, :3], prop)
+    eng.close()
+
+
 @pytest.mark.parametrize("name", ["libero_base", "libero_pro", "single_image"])
 def test_engine_matches_reference_golden(name):
     """The CUDA engine against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by

@@ -174,9 +174,17 @@ class VLAEngine:
         B, Lext = ext_ids.shape
         L = Lext - NUM_TOKENS - 1
         T, A = self.chunk_len, self.action_dim
-        assert pixel_values.dtype == torch.bfloat16 and pixel_values.is_contiguous()
-        if tuple(pixel_values.shape) != (B, 6 * self.n_images, 224, 224):
-            raise ValueError(f"pixel_values must be ({B}, {6 * self.n_images}, 224, 224), got {tuple(pixel_values.shape)}")
+        if pixel_values.dtype != torch.bfloat16 or not pixel_values.is_contiguous() or \
+                tuple(pixel_values.shape) != (B, 6 * self.n_images, 224, 224):
+            raise ValueError(f"pixel_values must be contiguous bf16 ({B}, {6 * self.n_images}, 224, 224), got "
+                             f"{pixel_values.dtype} {tuple(pixel_values.shape)}")
+        for name, t, dt, shape in (("ext_ids", ext_ids, torch.int64, (B, Lext)), ("aq_index", aq_index, torch.int32, (B, Lext)),
+                                   ("proprio", proprio, torch.float32, (B, self.proprio_dim))):
+            if t.dtype != dt or tuple(t.shape) != shape or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError(f"{name} must be a contiguous CUDA {dt} tensor of shape {shape}, got {t.dtype} "
+                                 f"{tuple(t.shape)} on {t.device}")
+        if not pixel_values.is_cuda:
+            raise ValueError("predict_device takes CUDA tensors (use predict_host for host buffers)")
         # The engine replays a CUDA graph keyed on (B, L, buffer addresses): write into buffers that stay put and
         # hand fresh copies (a few hundred bytes per sample) to the caller.
         key = (B, want_last_ha)
@@ -200,6 +208,11 @@ class VLAEngine:
                      out_last_ha: Optional[torch.Tensor] = None) -> None:
         """End-to-end call on HOST tensors (ideally pinned): H2D, forward, D2H, stream sync inside."""
         B, Lext = ext_ids.shape
+        if pixel_values.dtype != torch.bfloat16 or tuple(pixel_values.shape) != (B, 6 * self.n_images, 224, 224):
+            raise ValueError(f"pixel_values must be bf16 ({B}, {6 * self.n_images}, 224, 224), got {pixel_values.dtype} "
+                             f"{tuple(pixel_values.shape)}")
+        self._check_host_io(B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha)
+        pixel_values = pixel_values.contiguous()
         rc = self.lib.vla_predict_host(self._h, pixel_values.data_ptr(), ext_ids.data_ptr(), aq_index.data_ptr(),
                                        proprio.data_ptr(), B, Lext - NUM_TOKENS - 1, out_norm.data_ptr(),
                                        out_unnorm.data_ptr(),
@@ -216,6 +229,7 @@ class VLAEngine:
         if images_u8.dtype != torch.uint8 or tuple(images_u8.shape) != (B, self.n_images, 224, 224, 3):
             raise ValueError(f"images must be uint8 ({B}, {self.n_images}, 224, 224, 3), got {images_u8.dtype} "
                              f"{tuple(images_u8.shape)}")
+        self._check_host_io(B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha)
         images_u8 = images_u8.contiguous()
         rc = self.lib.vla_predict_host_u8(self._h, images_u8.data_ptr(), ext_ids.data_ptr(), aq_index.data_ptr(),
                                           proprio.data_ptr(), B, Lext - NUM_TOKENS - 1, out_norm.data_ptr(),
@@ -223,6 +237,24 @@ class VLAEngine:
                                           out_last_ha.data_ptr() if out_last_ha is not None else None,
                                           torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, self._h)
+
+    def _check_host_io(self, B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha) -> None:
+        """The C ABI takes raw pointers: every buffer it will read or write is checked here for dtype, size and
+        contiguity (the reference raises on mismatched batches, MP:519-522)."""
+        T, A = self.chunk_len, self.action_dim
+
+        def need(name, t, dtype, shape):
+            if t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous() or t.is_cuda:
+                raise ValueError(f"{name} must be a contiguous host {dtype} tensor of shape {tuple(shape)}, got "
+                                 f"{t.dtype} {tuple(t.shape)}")
+
+        need("ext_ids", ext_ids, torch.int64, (B, Lext))
+        need("aq_index", aq_index, torch.int32, (B, Lext))
+        need("proprio", proprio, torch.float32, (B, self.proprio_dim))
+        need("out_norm", out_norm, torch.float32, (B, T, A))
+        need("out_unnorm", out_unnorm, torch.float32, (B, T, A))
+        if out_last_ha is not None:
+            need("out_last_ha", out_last_ha, torch.bfloat16, (B, NUM_TOKENS, LLM_DIM))
 
     def set_image_norm(self, mean, std) -> None:
         """mean / std of the two backbones, each (2, 3): row 0 DINOv2, row 1 SigLIP (preprocessor_config.json)."""
