@@ -54,7 +54,13 @@ struct FaDev {
   __nv_bfloat16* out;
   int ld_out;
   unsigned int* trace;  // timing experiments only (VLA_FA_TRACE): [0] = count, then (event, clock) pairs of CTA 0
-  int debug;  // timing experiments only (VLA_FA_DEBUG): 1 = no softmax math, 2 = no PV MMAs, 4 = no QK MMAs
+  // timing experiments only (VLA_FA_DEBUG bit mask): 1 = softmax warps only move the barriers, 2 = no PV MMAs,
+  // 4 = no QK MMAs, 8 = no exp-phase turn taking, 16 = no early QK issue, 32 = no MUFU work, 64 = no TMEM loads,
+  // 128 = no P stores, 256 = no row-max exchange, 512 = no output stores, 1024 = no O loads.  Findings (Qwen shape,
+  // 140 us): removing the exponentials, the TMEM traffic and the exchange changes nothing (<= 3 %); the output stores
+  // cost ~10 %; bit 1 alone (no softmax code at all) gives 59 us - the kernel is bound by the latency of the per-tile
+  // dependency chain through the softmax warps, not by any one unit.
+  int debug;
   // per (sample, kv head): query head (relative to the group) and query tile of slot A / slot B, packed
   // hA | qA << 8 | hB << 16 | qB << 24; hB == 0xff: slot B idle
   uint32_t items[FA_MAX_ITEMS];
@@ -177,8 +183,16 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
   float mloc = -INFINITY;
   if (NLIVE > 0) {
 #pragma unroll
-    for (int c = 0; c < NLIVE; ++c) tmem_ld_32x32b_x32(tSh + c * 32, v[c]);
-    tmem_ld_wait();
+    if (p.debug & 64) {  // timing experiment: no TMEM loads
+#pragma unroll
+      for (int c = 0; c < NLIVE; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[c][i] = 0x3f000000u + i;
+    } else {
+#pragma unroll
+      for (int c = 0; c < NLIVE; ++c) tmem_ld_32x32b_x32(tSh + c * 32, v[c]);
+      tmem_ld_wait();
+    }
   }
   if (s_free_bar) {  // the scores are in registers: the MMA warp may overwrite S with the next tile's Q K^T
     tc_fence_before();
@@ -209,7 +223,7 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
   }
   // row max over the whole tile: one float per row each way, one 64-thread named barrier
   float m_new = fmaxf(m_ref, mloc);
-  if (SPLIT) {
+  if (SPLIT && !(p.debug & 256)) {
     *xch_mine = mloc;
     named_bar_sync(bar_id, 64);
     m_new = fmaxf(m_new, *xch_other);
@@ -254,8 +268,13 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2v, nmb);
-        v[c][2 * i] = __float_as_uint(ex2f(t.x));
-        v[c][2 * i + 1] = __float_as_uint(ex2f(t.y));
+        if (p.debug & 32) {  // timing experiment: no MUFU work
+          v[c][2 * i] = __float_as_uint(t.x);
+          v[c][2 * i + 1] = __float_as_uint(t.y);
+        } else {
+          v[c][2 * i] = __float_as_uint(ex2f(t.x));
+          v[c][2 * i + 1] = __float_as_uint(ex2f(t.y));
+        }
       }
       // phase 2: row sum (packed FADD2) and bf16 packing
       uint32_t pk[16];
@@ -265,7 +284,7 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
         sum2 = __fadd2_rn(sum2, e);
         pk[i] = pack_bf16(e.x, e.y);
       }
-      tmem_st_32x32b_x16(tPh + c * 16, pk);
+      if (!(p.debug & 128)) tmem_st_32x32b_x16(tPh + c * 16, pk);
     }
     l += sum2.x + sum2.y;
   }
@@ -666,7 +685,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       constexpr int GMAX = L::SPLIT ? G - G0 : G;
       uint32_t o[GMAX][8];
       const int g_lo = half ? G0 : 0, g_n = half ? G - G0 : G0;
-      if (warp_active) {
+      if (warp_active && !(p.debug & 1024)) {
 #pragma unroll
         for (int c = 0; c < GMAX; ++c)
           if (c < g_n) tmem_ld_32x32b_x8(tO + (g_lo + c) * 8, o[c]);
@@ -674,7 +693,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       }
       tc_fence_before();
       mbar_arrive(o_empty(x));  // O_x may be overwritten by the next item's first PV
-      if (warp_active && grow < p.Sq) {
+      if (warp_active && grow < p.Sq && !(p.debug & 512)) {
         const float inv = 1.0f / l_tot;
         __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.Sq + grow) * p.ld_out + it.h[x] * HD + g_lo * 8;
 #pragma unroll
