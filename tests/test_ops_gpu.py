@@ -173,6 +173,9 @@ def _ref_attention(qkv, B, S, H, HKV, hd, causal):
     (2, 128, 16, 16, 64, False),   # exactly one tile
     (1, 129, 14, 2, 64, True),     # one row into the second tile
     (2, 400, 16, 16, 72, True),
+    (2, 272, 12, 12, 64, False),   # 16 rows past two full tiles: tensor-core kernel + key-splitting kernel
+    (1, 400, 14, 2, 64, False),    # same with GQA
+    (3, 389, 12, 12, 64, False),   # 5 rows past three full tiles
 ])
 @pytest.mark.parametrize("impl", [1, 2])   # 1 = mma.sync kernel, 2 = tcgen05/TMEM kernel
 def test_attention(B, S, H, HKV, hd, causal, impl):

@@ -244,7 +244,7 @@ template <int HD, int HDP>
 __global__ void __launch_bounds__(ATT_THREADS)
 splitkv_attn_kernel(const __nv_bfloat16* __restrict__ qp, int ld_q, int Sq, const __nv_bfloat16* __restrict__ kp,
                     const __nv_bfloat16* __restrict__ vp, int ld, int S, int group, float scale_log2,
-                    __nv_bfloat16* __restrict__ out, int ld_out) {
+                    __nv_bfloat16* __restrict__ out, int ld_out, int q_rows) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int LDS = HDP + 8;
@@ -257,7 +257,7 @@ splitkv_attn_kernel(const __nv_bfloat16* __restrict__ qp, int ld_q, int Sq, cons
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / group;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __nv_bfloat16* gq = qp + static_cast<long long>(b) * Sq * ld_q + h * HD;
+  const __nv_bfloat16* gq = qp + static_cast<long long>(b) * q_rows * ld_q + h * HD;
   const __nv_bfloat16* gk = kp + static_cast<long long>(b) * S * ld + kvh * HD;
   const __nv_bfloat16* gv = vp + static_cast<long long>(b) * S * ld + kvh * HD;
   __nv_bfloat16* wK = sKV + warp * (4 * SK_BN * LDS);
@@ -426,14 +426,14 @@ splitkv_attn_kernel(const __nv_bfloat16* __restrict__ qp, int ld_q, int Sq, cons
       a1 += f * ov.y;
     }
     const float inv = 1.f / L;
-    *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * Sq + q0 + r) * ld_out + h * HD + c) =
+    *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * q_rows + q0 + r) * ld_out + h * HD + c) =
         pack_bf16(a0 * inv, a1 * inv);
   }
 }
 
 template <int HD, int HDP>
 int launch_splitkv(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ld,
-                   int B, int S, int n_heads, int group, __nv_bfloat16* out, int ld_out, cudaStream_t s,
+                   int B, int S, int n_heads, int group, __nv_bfloat16* out, int ld_out, int q_rows, cudaStream_t s,
                    const char** err) {
   constexpr int LDS = HDP + 8;
   constexpr int SMEM_TILES = (16 + 4 * 4 * SK_BN) * LDS * 2;
@@ -451,7 +451,7 @@ int launch_splitkv(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(HD))) * 1.4426950408889634f;
   dim3 grid((Sq + 15) / 16, n_heads, B);
   launch_kernel(splitkv_attn_kernel<HD, HDP>, dim3(grid), dim3(ATT_THREADS), SMEM, s, q, ld_q, Sq, k, v, ld, S, group,
-                scale_log2, out, ld_out);
+                scale_log2, out, ld_out, q_rows);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = cudaGetErrorString(e);
@@ -521,13 +521,26 @@ int cross_attention_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_
   }
   // The large shapes (hd 64 / 72, at least one full-ish query tile) run on the tcgen05 kernel (attention_tc.cu).
   if (g_attn_impl != 1 && (hd == 64 || hd == 72) && (Sq >= 32 || g_attn_impl == 2)) {
-    const int rc = attention_tc_launch(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, hd, causal, out, ld_out, s, err);
+    // A few query rows past the last full 128-row tile (DINOv2: 261 = 2 x 128 + 5) would occupy a whole tcgen05 work
+    // item - a 128-row MMA tile and every K/V tile of the head - for a handful of rows.  Those rows go to the
+    // key-splitting kernel instead, the full tiles to the tensor-core kernel; both see all the keys.
+    const int rem = Sq % 128;
+    static const bool no_split = getenv("VLA_FA_NO_ROW_SPLIT") != nullptr;
+    if (!causal && hd == 64 && Sq > 128 && rem > 0 && rem <= 16 && Skv >= 128 && !no_split) {
+      const int full = Sq - rem;
+      int rc = attention_tc_launch(q, ld_q, full, k, v, ld_kv, Skv, B, n_heads, group, hd, 0, out, ld_out, Sq, s, err);
+      if (rc < 0) return rc;
+      if (rc == 0)
+        return launch_splitkv<64, 64>(q + static_cast<long long>(full) * ld_q, ld_q, rem, k, v, ld_kv, B, Skv, n_heads,
+                                      group, out + static_cast<long long>(full) * ld_out, ld_out, Sq, s, err);
+    }
+    const int rc = attention_tc_launch(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, hd, causal, out, ld_out, Sq, s, err);
     if (rc <= 0) return rc;
   }
   // few queries against many keys (the policy's Bridge-Attention): the warps split the keys instead of the queries
   if (!causal && Sq <= 32 && Skv >= 128 && g_attn_impl != 1 && !(ld_out & 1)) {
-    if (hd == 112) return launch_splitkv<112, 112>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, out, ld_out, s, err);
-    if (hd == 64) return launch_splitkv<64, 64>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, out, ld_out, s, err);
+    if (hd == 112) return launch_splitkv<112, 112>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, out, ld_out, Sq, s, err);
+    if (hd == 64) return launch_splitkv<64, 64>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, out, ld_out, Sq, s, err);
   }
   if (hd == 64) return launch_attn<64, 64>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, causal, out, ld_out, s, err);
   if (hd == 72) return launch_attn<72, 80>(q, ld_q, Sq, k, v, ld_kv, B, Skv, n_heads, group, causal, out, ld_out, s, err);

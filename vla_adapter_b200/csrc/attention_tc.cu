@@ -47,6 +47,7 @@ constexpr int FA_MAX_ITEMS = 24;               // work items per (sample, kv hea
 
 struct FaDev {
   int Sq, Skv, group, kv_heads, causal;
+  int q_rows;  // rows between two samples of Q / out (>= Sq: the caller may hand a row range of each sample)
   int bn;       // keys per tile (64: two CTAs per SM, 128: one)
   int n_bg;     // samples * kv heads
   int n_items;  // n_bg * items per (sample, kv head)
@@ -305,7 +306,7 @@ struct FaSmem {
   static constexpr int SM_WARPS = SPLIT ? 8 : 4;             // softmax warps per slot
   static constexpr int THREADS = 128 + 2 * SM_WARPS * 32;   // warpgroup 0 (TMA, MMA, 2 idle warps) + softmax warps
   static constexpr int SM_THREADS = SM_WARPS * 32;
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = TAIL ? 2 : 3;  // head dim 72: two 40 KB stages leave room for the epilogue staging
   static constexpr int QBUFS = 4;  // 2 slots x 2 buffers: the next item's Q tiles land while this item computes
   static constexpr uint32_t KV_TILE = BN * 128;  // BN keys x 64 bf16
   static constexpr uint32_t KV_TAIL = BN * 32;   // BN keys x 16 bf16
@@ -320,7 +321,14 @@ struct FaSmem {
   static constexpr uint32_t OFF_VT = OFF_KT + STAGES * KV_TAIL;
   static constexpr uint32_t OFF_BAR = TAIL ? OFF_VT + STAGES * KV_TAIL : OFF_QT;
   static constexpr uint32_t OFF_XCH = OFF_BAR + 256;  // row-max / row-sum exchange: [slot][parity][half][128] floats
-  static constexpr uint32_t TOTAL = OFF_XCH + (SPLIT ? 2 * 2 * 2 * 128 * 4 : 0);  // dynamic array is __align__(1024)
+  static constexpr uint32_t XCH_END = OFF_XCH + (SPLIT ? 2 * 2 * 2 * 128 * 4 : 0);
+  // Head dim 64, 128-key tiles: the epilogue leaves through shared memory and one TMA store per warp (32 rows x 32
+  // columns, 64B-swizzled, 2 KB per softmax warp) - the per-thread 16-byte row stores took ~3k cycles per item during
+  // which the slot's next item could not start.  Head dim 72: columns [0, 64) leave that way, the warp of the
+  // second half stores the last 8 columns itself.
+  static constexpr bool TMA_EPI = SPLIT;
+  static constexpr uint32_t OFF_STG = (XCH_END + 1023u) & ~1023u;
+  static constexpr uint32_t TOTAL = TMA_EPI ? OFF_STG + 2 * SM_WARPS * 2048 : XCH_END;  // dynamic array is __align__(1024)
   // TMEM columns: S_A [0,BN), S_B [BN,2BN) (P aliases the first half of S), then O_A, O_B
   // Head dim 64 has room for P OUTSIDE the score columns (S_A S_B | P_A P_B | O_A O_B = 256 + 128 + 128): the next
   // tile's QK^T is issued as soon as the softmax warps have read the scores, and PV of this tile runs beside the
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__((FaSmem<HD, BN>::THREADS), (FaSmem<HD, BN>::CT
 fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                   const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapQt,
                   const __grid_constant__ CUtensorMap mapKt, const __grid_constant__ CUtensorMap mapVt,
-                  const __grid_constant__ FaDev p) {
+                  const __grid_constant__ CUtensorMap mapO, const __grid_constant__ FaDev p) {
   using L = FaSmem<HD, BN>;
   constexpr bool TAIL = L::TAIL;
   constexpr int NS = L::STAGES;
@@ -693,9 +701,45 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       }
       tc_fence_before();
       mbar_arrive(o_empty(x));  // O_x may be overwritten by the next item's first PV
-      if (warp_active && grow < p.Sq && !(p.debug & 512)) {
+      if constexpr (L::TMA_EPI) {
+        if (warp_active && !(p.debug & 512)) {  // rows past Sq are clipped by the TMA unit
+          const float inv = 1.0f / l_tot;
+          const uint32_t stg = sbase + L::OFF_STG + static_cast<uint32_t>(warp_idx - 4) * 2048u;
+          if (lane == 0) tma_store_wait_read<0>();  // the previous item's store has left this buffer
+          __syncwarp();
+          const uint32_t row_addr = stg + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t w0 = pack_bf16(__uint_as_float(o[c][0]) * inv, __uint_as_float(o[c][1]) * inv);
+            const uint32_t w1 = pack_bf16(__uint_as_float(o[c][2]) * inv, __uint_as_float(o[c][3]) * inv);
+            const uint32_t w2 = pack_bf16(__uint_as_float(o[c][4]) * inv, __uint_as_float(o[c][5]) * inv);
+            const uint32_t w3 = pack_bf16(__uint_as_float(o[c][6]) * inv, __uint_as_float(o[c][7]) * inv);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((c ^ sw) << 4)), "r"(w0),
+                         "r"(w1), "r"(w2), "r"(w3)
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&mapO, stg, it.h[x] * HD + g_lo * 8, wrow0, it.b);
+            tma_store_commit();
+          }
+          if constexpr (GMAX > 4) {  // head dim 72: columns [64, 72) of the row
+            if (half && grow < p.Sq) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(o[4][0]) * inv, __uint_as_float(o[4][1]) * inv);
+              w.y = pack_bf16(__uint_as_float(o[4][2]) * inv, __uint_as_float(o[4][3]) * inv);
+              w.z = pack_bf16(__uint_as_float(o[4][4]) * inv, __uint_as_float(o[4][5]) * inv);
+              w.w = pack_bf16(__uint_as_float(o[4][6]) * inv, __uint_as_float(o[4][7]) * inv);
+              *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(it.b) * p.q_rows + grow) * p.ld_out +
+                                        it.h[x] * HD + 64) = w;
+            }
+          }
+        }
+      } else if (warp_active && grow < p.Sq && !(p.debug & 512)) {
         const float inv = 1.0f / l_tot;
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.Sq + grow) * p.ld_out + it.h[x] * HD + g_lo * 8;
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.q_rows + grow) * p.ld_out + it.h[x] * HD + g_lo * 8;
 #pragma unroll
         for (int c = 0; c < GMAX; ++c) {
           if (c < g_n) {
@@ -711,6 +755,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     }
   }
 
+  if (L::TMA_EPI && warp_idx >= 4 && lane == 0) tma_store_wait<0>();  // output stores have left shared memory
   tc_fence_before();
   __syncthreads();
   if (warp_idx == 1) {
@@ -739,13 +784,14 @@ EncodeTiledFn fa_encode_fn() {
 
 // Per-head 4-D view (d, head, row, sample) of a [samples*rows, ld] bf16 matrix whose head h sits at column h*hd.
 bool make_head_map(CUtensorMap* m, const void* base, int hd, int heads, int rows, int samples, int ld, int box_d,
-                   int box_rows, CUtensorMapSwizzle swz) {
+                   int box_rows, CUtensorMapSwizzle swz, int sample_rows = 0) {
+  if (!sample_rows) sample_rows = rows;
   EncodeTiledFn fn = fa_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(hd), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(rows),
                         static_cast<cuuint64_t>(samples)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(hd) * 2, static_cast<cuuint64_t>(ld) * 2,
-                           static_cast<cuuint64_t>(rows) * ld * 2};
+                           static_cast<cuuint64_t>(sample_rows) * ld * 2};
   cuuint32_t box[4] = {static_cast<cuuint32_t>(box_d), 1, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -795,8 +841,8 @@ int build_items(int Sq, int Skv, int group, int causal, int bn, uint32_t* items)
 
 template <int HD, int BN>
 int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ld_kv,
-              int Skv, int B, int n_heads, int group, int causal, __nv_bfloat16* out, int ld_out, cudaStream_t s,
-              const char** err) {
+              int Skv, int B, int n_heads, int group, int causal, __nv_bfloat16* out, int ld_out, int q_rows,
+              cudaStream_t s, const char** err) {
   using L = FaSmem<HD, BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -812,11 +858,11 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
   const int per_bg = build_items(Sq, Skv, group, causal, BN, p.items);
   if (per_bg < 0) return 1;
   CUtensorMap mQ, mK, mV, mQt, mKt, mVt;
-  bool ok = make_head_map(&mQ, q, HD, n_heads, Sq, B, ld_q, 64, FA_BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+  bool ok = make_head_map(&mQ, q, HD, n_heads, Sq, B, ld_q, 64, FA_BM, CU_TENSOR_MAP_SWIZZLE_128B, q_rows) &&
             make_head_map(&mK, k, HD, kv_heads, Skv, B, ld_kv, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B) &&
             make_head_map(&mV, v, HD, kv_heads, Skv, B, ld_kv, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (ok && L::TAIL) {
-    ok = make_head_map(&mQt, q, HD, n_heads, Sq, B, ld_q, 16, FA_BM, CU_TENSOR_MAP_SWIZZLE_32B) &&
+    ok = make_head_map(&mQt, q, HD, n_heads, Sq, B, ld_q, 16, FA_BM, CU_TENSOR_MAP_SWIZZLE_32B, q_rows) &&
          make_head_map(&mKt, k, HD, kv_heads, Skv, B, ld_kv, 16, BN, CU_TENSOR_MAP_SWIZZLE_32B) &&
          make_head_map(&mVt, v, HD, kv_heads, Skv, B, ld_kv, 16, BN, CU_TENSOR_MAP_SWIZZLE_32B);
   } else if (ok) {
@@ -824,12 +870,24 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
     mKt = mK;
     mVt = mV;
   }
+  CUtensorMap mO = mQ;
+  if (ok && L::TMA_EPI) {  // (column, row, sample) view of the output, 32 x 32 boxes in the staging layout
+    EncodeTiledFn fn = fa_encode_fn();
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(n_heads) * HD, static_cast<cuuint64_t>(Sq), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_out) * 2, static_cast<cuuint64_t>(q_rows) * ld_out * 2};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    ok = fn(&mO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   if (!ok) {
     if (err) *err = "attention: cuTensorMapEncodeTiled failed";
     return -4;
   }
   p.bn = BN;
   p.Sq = Sq;
+  p.q_rows = q_rows;
   p.Skv = Skv;
   p.group = group;
   p.kv_heads = kv_heads;
@@ -850,7 +908,7 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
     cudaMemsetAsync(p.trace, 0, 32004 * sizeof(unsigned int), s);
   }
   const int grid = std::min(p.n_items, L::CTAS_PER_SM * fa_num_sms());
-  launch_kernel(fa_tcgen05_kernel<HD, BN>, dim3(grid), dim3(L::THREADS), L::TOTAL, s, mQ, mK, mV, mQt, mKt, mVt, p);
+  launch_kernel(fa_tcgen05_kernel<HD, BN>, dim3(grid), dim3(L::THREADS), L::TOTAL, s, mQ, mK, mV, mQt, mKt, mVt, mO, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = cudaGetErrorString(e);
@@ -879,16 +937,17 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
 // Returns 1 when the shape is not served by this kernel (caller falls back to the mma.sync kernel), 0 on launch.
 int attention_tc_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v,
                         int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal, __nv_bfloat16* out,
-                        int ld_out, cudaStream_t s, const char** err) {
+                        int ld_out, int q_rows, cudaStream_t s, const char** err) {
+  if (q_rows < Sq) q_rows = Sq;
   if ((ld_out & 7) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
   static int bn64 = -1;  // VLA_FA_BN64=1: 64-key tiles, two CTAs per SM (experiment switch)
   if (bn64 < 0) {
     const char* e = getenv("VLA_FA_BN64");
     bn64 = e ? atoi(e) : 0;
   }
-  if (hd == 64 && bn64) return launch_fa<64, 64>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
-  if (hd == 64) return launch_fa<64, 128>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
-  if (hd == 72) return launch_fa<72, 128>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, s, err);
+  if (hd == 64 && bn64) return launch_fa<64, 64>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, q_rows, s, err);
+  if (hd == 64) return launch_fa<64, 128>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, q_rows, s, err);
+  if (hd == 72) return launch_fa<72, 128>(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, causal, out, ld_out, q_rows, s, err);
   return 1;
 }
 

@@ -45,7 +45,7 @@ int cross_attention_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_
 // tcgen05/TMEM/TMA flash attention (attention_tc.cu) for hd in {64, 72}; returns 1 if the shape is not served.
 int attention_tc_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v,
                         int ld_kv, int Skv, int B, int n_heads, int group, int hd, int causal, __nv_bfloat16* out,
-                        int ld_out, cudaStream_t s, const char** err);
+                        int ld_out, int q_rows, cudaStream_t s, const char** err);  // q_rows: rows between samples of q/out
 // 0 = auto (tcgen05 for hd 64/72 with Sq >= 32, mma.sync otherwise), 1 = mma.sync only, 2 = tcgen05 whenever possible
 void attention_set_impl(int impl);
 
