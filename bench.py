@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--variant", default="base", choices=["base", "pro"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=200.0, help="wall-clock bound [s] of the reference arm")
-    ap.add_argument("--latency-iters", type=int, default=30)
+    ap.add_argument("--latency-iters", type=int, default=200, help="bs=1 latency samples (after 20 warm-up calls)")
     ap.add_argument("--chunk", default="8x7x8", help="chunk_len x action_dim x proprio_dim: 8x7x8 = LIBERO / CALVIN "
                     "(constants.py:28-40), 25x14x14 = the reference's larger-chunk preset (ALOHA, constants.py:42-47)")
     args = ap.parse_args()
@@ -345,15 +345,16 @@ def main():
     lat = []
     one = [t[:1].contiguous().pin_memory() for t in (pix_h, ext_h, aq_h, prop_h)]
     o1, o2 = on_h[:1].clone().pin_memory(), ou_h[:1].clone().pin_memory()
-    for i in range(args.latency_iters + 5 if args.latency_iters > 0 else 0):
+    for i in range(args.latency_iters + 20 if args.latency_iters > 0 else 0):
         t0 = time.perf_counter()
         eng.predict_host(one[0], one[1], one[2], one[3], o1, o2)
-        if i >= 5:
+        if i >= 20:
             lat.append((time.perf_counter() - t0) * 1e3)
     lat.sort()
     latency = None
     if lat:
         latency = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "iters": len(lat),
+                   "warmup": 20,
                    "how": "wall clock around vla_predict_host(B=1) incl. H2D/D2H and stream sync"}
 
     # ---------------- CPU baseline (rank 0, N=1 only): the oracle on this box's cores, bounded sample

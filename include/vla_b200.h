@@ -164,6 +164,19 @@ int vla_op_layernorm(const void* x, int rows, int dim, int ldx, const float* w, 
 int vla_op_rmsnorm(const void* x, int rows, int dim, int ldx, const float* w, float eps, void* y,
                    int ldy, void* stream);
 
+/* A LayerNorm / RMSNorm in front of a Linear, folded into the GEMM (how the engine runs norm1 -> qkv, norm2 -> fc1,
+ * input_layernorm -> q|k|v and post_attention_layernorm -> gate|up; csrc/gemm.cuh GemmArgs::row_stats).
+ * vla_op_fold_norm, once per weight: W[n,k] <- bf16(W[n,k] * norm_w[k]) IN PLACE, bias[n] += sum_k W[n,k] norm_b[k]
+ *   (norm_b NULL for RMSNorm; bias fp32, required when norm_b is given), colsum[n] = sum_k W'[n,k] (fp32, may be NULL
+ *   for RMSNorm).
+ * vla_op_norm_gemm: C = act(Linear(Norm(x))) from the RAW rows x [rows, K] and the folded W / bias / colsum;
+ *   rms != 0 selects RMSNorm; stats is scratch for 2*rows floats. act as in vla_op_gemm (3 = SwiGLU, RMSNorm only). */
+int vla_op_fold_norm(void* W, int N, int K, int ldw, const float* norm_w, const float* norm_b, float* bias,
+                     float* colsum, void* stream);
+int vla_op_norm_gemm(const void* x, int rows, int ldx, const void* W, int ldw, int N, int K, void* C, int ldc,
+                     const float* bias, const float* colsum, int rms, float eps, int act, float* stats,
+                     void* stream);
+
 /* Multi-head attention over a packed qkv buffer.
  *   q at qkv[row, q_off + h*hd], k at qkv[row, k_off + (h/group)*hd], v likewise; row = b*S + s.
  *   hd in {64, 72}; causal != 0 applies the lower-triangular mask; scale = hd^-0.5. */

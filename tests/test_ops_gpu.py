@@ -151,6 +151,55 @@ def test_rmsnorm():
     assert (y.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("rows,dim,N,act", [(777, 1024, 3072, "none"), (1000, 1152, 4304, "gelu"), (261, 1024, 4096, "gelu"),
+                                            (33, 1152, 3456, "none")])
+def test_layernorm_folded_into_gemm(rows, dim, N, act):
+    """norm1 -> qkv / norm2 -> fc1 of the ViT blocks: LayerNorm folded into the GEMM (row statistics in the epilogue,
+    W * diag(g), bias + W b) against the fp32 LayerNorm -> Linear, and against the unfolded kernel pair."""
+    from vla_adapter_b200 import ops
+
+    x = _randn(rows, dim, seed=41) * 3 + 0.7          # non-zero mean: the mean term of the fold matters
+    x[:, 5] += 40.0                                   # an outlier channel, as in real ViT residual streams
+    g = (torch.randn(dim, device="cuda") * 0.3 + 1).float()
+    b = (torch.randn(dim, device="cuda") * 0.2).float()
+    W = _randn(N, dim, scale=dim ** -0.5, seed=42)
+    bias = torch.randn(N, device="cuda")
+    out = ops.norm_linear(x, g, b, W, bias, 1e-6, act)
+    ref = torch.nn.functional.layer_norm(x.float(), (dim,), g, b, 1e-6) @ W.float().T + bias
+    if act == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    two_step = ops.linear(ops.layernorm(x, g, b, 1e-6), W, bias=bias, act=act)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 5e-3
+    assert _rel(out, ref) < 1.5 * _rel(two_step, ref) + 1e-4   # no worse than rounding the normalised rows to bf16
+
+
+@pytest.mark.parametrize("act", ["none", "swiglu"])
+def test_rmsnorm_folded_into_gemm(act):
+    from vla_adapter_b200 import ops
+
+    rows, dim = 1250, 896
+    x = _randn(rows, dim, seed=43) * 2
+    x[:, 7] *= 30.0
+    g = (torch.randn(dim, device="cuda") * 0.1 + 1).float()
+    xf = x.float()
+    xn = g * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6))
+    if act == "swiglu":
+        I = 4864
+        wg = _randn(I, dim, scale=dim ** -0.5, seed=44)
+        wu = _randn(I, dim, scale=dim ** -0.5, seed=45)
+        W = torch.stack([wg.view(I // 16, 16, dim), wu.view(I // 16, 16, dim)], dim=1).reshape(2 * I, dim).contiguous()
+        out = ops.norm_linear(x, g, None, W, None, 1e-6, act)
+        ref = torch.nn.functional.silu(xn @ wg.float().T) * (xn @ wu.float().T)
+    else:
+        W = _randn(1152, dim, scale=dim ** -0.5, seed=46)
+        bias = torch.randn(1152, device="cuda")
+        out = ops.norm_linear(x, g, None, W, bias, 1e-6, act)
+        ref = xn @ W.float().T + bias
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 5e-3
+
+
 def _ref_attention(qkv, B, S, H, HKV, hd, causal):
     q, k, v = qkv.float().split([H * hd, HKV * hd, HKV * hd], dim=-1)
     q = q.view(B, S, H, hd).transpose(1, 2)

@@ -66,6 +66,39 @@ int vla_op_layernorm(const void* x, int rows, int dim, int ldx, const float* w, 
   return rc ? fail(rc, err) : 0;
 }
 
+int vla_op_fold_norm(void* W, int N, int K, int ldw, const float* norm_w, const float* norm_b, float* bias,
+                     float* colsum, void* stream) {
+  const char* err = nullptr;
+  int rc = vla::fold_norm_launch(static_cast<__nv_bfloat16*>(W), N, K, ldw, norm_w, norm_b, bias, colsum,
+                                 static_cast<cudaStream_t>(stream), &err);
+  return rc ? fail(rc, err) : 0;
+}
+
+int vla_op_norm_gemm(const void* x, int rows, int ldx, const void* W, int ldw, int N, int K, void* C, int ldc,
+                     const float* bias, const float* colsum, int rms, float eps, int act, float* stats,
+                     void* stream) {
+  const char* err = nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = vla::row_stats_launch(static_cast<const __nv_bfloat16*>(x), rows, K, ldx, rms, eps, stats, s, &err);
+  if (rc) return fail(rc, err);
+  vla::GemmArgs g;
+  g.A = static_cast<const __nv_bfloat16*>(x);
+  g.lda = ldx;
+  g.rows = rows;
+  g.W = static_cast<const __nv_bfloat16*>(W);
+  g.ldw = ldw;
+  g.N = N;
+  g.K = K;
+  g.C = static_cast<__nv_bfloat16*>(C);
+  g.ldc = ldc;
+  g.bias = bias;
+  g.act = act;
+  g.row_stats = stats;
+  g.colsum = rms ? nullptr : colsum;
+  rc = vla::gemm_launch(g, s, &err);
+  return rc ? fail(rc, err) : 0;
+}
+
 int vla_op_rmsnorm(const void* x, int rows, int dim, int ldx, const float* w, float eps, void* y, int ldy,
                    void* stream) {
   const char* err = nullptr;

@@ -42,6 +42,7 @@ struct Master {
 struct VitBlock {
   float *ln1w, *ln1b, *bqkv, *bproj, *ls1, *ln2w, *ln2b, *bfc1, *bfc2, *ls2;
   bf16 *wqkv, *wproj, *wfc1, *wfc2;
+  float *cs_qkv = nullptr, *cs_fc1 = nullptr;  // column sums of the norm-folded wqkv / wfc1 (fold_norms)
 };
 struct Tower {
   int D, F, heads, hd, tokens, prefix, depth;
@@ -115,6 +116,7 @@ struct vla_engine {
   int maxB = 0, maxL = 0, maxS = 0;
   struct TowerWs {
     bf16 *col, *x, *xn, *qkv, *attn, *h;
+    float* stats;  // (rstd, -mean * rstd) per row for the GEMM that follows a folded norm
   };
   TowerWs tw[2];  // one workspace per vision tower: at small batch the towers run concurrently on two streams
   bf16 *w_patches, *w_ph1, *w_ph2;
@@ -162,6 +164,10 @@ struct vla_engine {
   cudaStream_t gstream = nullptr;
   cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   int use_graphs = 1;
+  // LayerNorm / RMSNorm in front of a GEMM folded into that GEMM (weights pre-scaled at finalize, per-row statistics
+  // applied in its epilogue): the normalised activations are never written.  VLA_NO_NORM_FOLD=1 keeps the norm kernels.
+  int fold_norms = 1;
+  float* l_stats = nullptr;
   // segment timing (vla_segment_times): events at the subsystem boundaries of the last EAGER forward
   int seg_on = 0;
   cudaEvent_t seg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -306,9 +312,15 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
   for (int i = 0; i < nblk; ++i) {
     const VitBlock& k = t.blocks[i];
     const bool last = (i == nblk - 1);
-    CK(vla::layernorm_launch(x, M, D, D, k.ln1w, k.ln1b, VIT_EPS, ws.xn, D, s, &_err));
     vla::GemmArgs g;
-    g.A = ws.xn; g.lda = D; g.rows = M; g.W = k.wqkv; g.ldw = D; g.N = 3 * D; g.K = D;
+    if (e->fold_norms) {  // norm1 lives in wqkv / bqkv / cs_qkv; only the row statistics are computed here
+      CK(vla::row_stats_launch(x, M, D, D, 0, VIT_EPS, ws.stats, s, &_err));
+      g.A = x; g.row_stats = ws.stats; g.colsum = k.cs_qkv;
+    } else {
+      CK(vla::layernorm_launch(x, M, D, D, k.ln1w, k.ln1b, VIT_EPS, ws.xn, D, s, &_err));
+      g.A = ws.xn;
+    }
+    g.lda = D; g.rows = M; g.W = k.wqkv; g.ldw = D; g.N = 3 * D; g.K = D;
     g.C = ws.qkv; g.ldc = 3 * D; g.bias = k.bqkv;
     CK(vla::gemm_launch(g, s, &_err));
     CK(vla::attention_launch(ws.qkv, 3 * D, 0, D, 2 * D, slabs, t.tokens, t.heads, 1, t.hd, 0, ws.attn, D, s, &_err));
@@ -316,9 +328,15 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
     g.A = ws.attn; g.lda = D; g.rows = M; g.W = k.wproj; g.ldw = D; g.N = D; g.K = D;
     g.C = x; g.ldc = D; g.bias = k.bproj; g.colscale = k.ls1; g.resid = x; g.ldr = D;
     CK(vla::gemm_launch(g, s, &_err));
-    CK(vla::layernorm_launch(x, M, D, D, k.ln2w, k.ln2b, VIT_EPS, ws.xn, D, s, &_err));
     g = vla::GemmArgs();
-    g.A = ws.xn; g.lda = D; g.rows = M; g.W = k.wfc1; g.ldw = D; g.N = F; g.K = D;
+    if (e->fold_norms) {
+      CK(vla::row_stats_launch(x, M, D, D, 0, VIT_EPS, ws.stats, s, &_err));
+      g.A = x; g.row_stats = ws.stats; g.colsum = k.cs_fc1;
+    } else {
+      CK(vla::layernorm_launch(x, M, D, D, k.ln2w, k.ln2b, VIT_EPS, ws.xn, D, s, &_err));
+      g.A = ws.xn;
+    }
+    g.lda = D; g.rows = M; g.W = k.wfc1; g.ldw = D; g.N = F; g.K = D;
     g.C = ws.h; g.ldc = F; g.bias = k.bfc1; g.act = vla::ACT_GELU;
     CK(vla::gemm_launch(g, s, &_err));
     g = vla::GemmArgs();
@@ -427,9 +445,15 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     const LlmLayer& w = e->llm[l];
     const bf16* xin = e->hid[l];
     bf16* xout = (l == NL - 1) ? e->l_tmp : e->hid[l + 1];
-    CK(vla::rmsnorm_launch(xin, M, D_LLM, D_LLM, w.ln1, LLM_EPS, e->l_xn, D_LLM, s, &_err));
     vla::GemmArgs g;
-    g.A = e->l_xn; g.lda = D_LLM; g.rows = M; g.W = w.wqkv; g.ldw = D_LLM; g.N = QKV_LLM; g.K = D_LLM;
+    if (e->fold_norms) {
+      CK(vla::row_stats_launch(xin, M, D_LLM, D_LLM, 1, LLM_EPS, e->l_stats, s, &_err));
+      g.A = xin; g.row_stats = e->l_stats;
+    } else {
+      CK(vla::rmsnorm_launch(xin, M, D_LLM, D_LLM, w.ln1, LLM_EPS, e->l_xn, D_LLM, s, &_err));
+      g.A = e->l_xn;
+    }
+    g.lda = D_LLM; g.rows = M; g.W = w.wqkv; g.ldw = D_LLM; g.N = QKV_LLM; g.K = D_LLM;
     g.C = e->l_qkv; g.ldc = QKV_LLM; g.bias = w.bqkv;
     // Small batch: RoPE of the q and k heads rides in this GEMM's epilogue (one kernel less on the critical path).
     // At bs=64 the rotation makes the epilogue the pacing stage (measured 148 us fused against 66 + 40 us), so the
@@ -445,9 +469,15 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     g.A = e->l_attn; g.lda = D_LLM; g.rows = M; g.W = w.wo; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
     g.C = xout; g.ldc = D_LLM; g.resid = xin; g.ldr = D_LLM;
     CK(vla::gemm_launch(g, s, &_err));
-    CK(vla::rmsnorm_launch(xout, M, D_LLM, D_LLM, w.ln2, LLM_EPS, e->l_xn, D_LLM, s, &_err));
     g = vla::GemmArgs();
-    g.A = e->l_xn; g.lda = D_LLM; g.rows = M; g.W = w.wgu; g.ldw = D_LLM; g.N = 2 * I_LLM; g.K = D_LLM;
+    if (e->fold_norms) {
+      CK(vla::row_stats_launch(xout, M, D_LLM, D_LLM, 1, LLM_EPS, e->l_stats, s, &_err));
+      g.A = xout; g.row_stats = e->l_stats;
+    } else {
+      CK(vla::rmsnorm_launch(xout, M, D_LLM, D_LLM, w.ln2, LLM_EPS, e->l_xn, D_LLM, s, &_err));
+      g.A = e->l_xn;
+    }
+    g.lda = D_LLM; g.rows = M; g.W = w.wgu; g.ldw = D_LLM; g.N = 2 * I_LLM; g.K = D_LLM;
     g.C = e->l_act; g.ldc = I_LLM; g.act = vla::ACT_SWIGLU;
     CK(vla::gemm_launch(g, s, &_err));
     g = vla::GemmArgs();
@@ -545,6 +575,7 @@ int vla_create(const vla_cfg* cfg, vla_engine** out) {
   e->cfg = *cfg;
   *out = e;
   if (const char* ng = getenv("VLA_NO_GRAPH")) e->use_graphs = atoi(ng) ? 0 : 1;
+  if (const char* nf = getenv("VLA_NO_NORM_FOLD")) e->fold_norms = atoi(nf) ? 0 : 1;
   const vla_cfg& c = e->cfg;
   if (c.n_images < 1 || c.n_images > 3) return e->fail(VLA_ERR_INVALID, "n_images must be 1..3");
   if (c.chunk_len < 1 || c.chunk_len > 32) return e->fail(VLA_ERR_INVALID, "chunk_len must be 1..32");
@@ -758,6 +789,26 @@ int vla_finalize(vla_engine* e) {
       if (rc) return e->fail(rc, err ? err : "x0 precompute failed");
     }
 
+    // ---- norms in front of GEMMs folded into the GEMM weights (once; see fold_norms)
+    if (e->fold_norms) {
+      const char* err = nullptr;
+      int rc = 0;
+      for (Tower* t : {&e->dino, &e->sig}) {
+        for (VitBlock& k : t->blocks) {
+          k.cs_qkv = e->dalloc<float>(3 * t->D);
+          k.cs_fc1 = e->dalloc<float>(t->F);
+          if (!rc) rc = vla::fold_norm_launch(k.wqkv, 3 * t->D, t->D, t->D, k.ln1w, k.ln1b, k.bqkv, k.cs_qkv, nullptr, &err);
+          if (!rc) rc = vla::fold_norm_launch(k.wfc1, t->F, t->D, t->D, k.ln2w, k.ln2b, k.bfc1, k.cs_fc1, nullptr, &err);
+        }
+      }
+      for (LlmLayer& w : e->llm) {
+        if (!rc) rc = vla::fold_norm_launch(w.wqkv, QKV_LLM, D_LLM, D_LLM, w.ln1, nullptr, nullptr, nullptr, nullptr, &err);
+        if (!rc) rc = vla::fold_norm_launch(w.wgu, 2 * I_LLM, D_LLM, D_LLM, w.ln2, nullptr, nullptr, nullptr, nullptr, &err);
+      }
+      if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = VLA_ERR_CUDA;
+      if (rc) return e->fail(rc, err ? err : "norm fold failed");
+    }
+
     // ---- workspace
     const int B = c.max_batch, L = c.max_prompt_len, n = c.n_images;
     const int S = e->NP + L + N_AQ + 1;
@@ -769,6 +820,7 @@ int vla_finalize(vla_engine* e) {
       e->tw[t].col = e->dalloc<bf16>(slabs * 256 * KP);
       e->tw[t].x = e->dalloc<bf16>(Mv * D);
       e->tw[t].xn = e->dalloc<bf16>(Mv * D);
+      e->tw[t].stats = e->dalloc<float>(2 * Mv);
       e->tw[t].qkv = e->dalloc<bf16>(Mv * 3 * D);
       e->tw[t].attn = e->dalloc<bf16>(Mv * D);
       e->tw[t].h = e->dalloc<bf16>(Mv * F);
@@ -780,6 +832,7 @@ int vla_finalize(vla_engine* e) {
     for (int i = 0; i <= c.llm_layers; ++i) e->hid.push_back(e->dalloc<bf16>(Ml * D_LLM));
     e->l_tmp = e->dalloc<bf16>(Ml * D_LLM);
     e->l_xn = e->dalloc<bf16>(Ml * D_LLM);
+    e->l_stats = e->dalloc<float>(2 * Ml);
     e->l_qkv = e->dalloc<bf16>(Ml * QKV_LLM);
     e->l_attn = e->dalloc<bf16>(Ml * D_LLM);
     e->l_act = e->dalloc<bf16>(Ml * I_LLM);

@@ -56,6 +56,8 @@ struct GemmDev {
   const float* rope_cos;  // RoPE fused into the epilogue (see GemmArgs)
   const float* rope_sin;
   int rope_cols, rope_S;
+  const float2* row_stats;  // normalisation of A folded into the epilogue (see GemmArgs)
+  const float* colsum;
 };
 
 VLA_DEVINL void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
@@ -260,6 +262,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       }
       const bool live = p.pack ? b < p.batches : r0 < p.rows;
       const int n0 = n_idx * p.bn + half * wcols;
+      float2 rst = make_float2(1.f, 0.f);  // this thread's row: (rstd, -mean * rstd)
+      if (p.row_stats && r0 + lane < p.rows) rst = __ldg(p.row_stats + r0 + lane);
 
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -279,8 +283,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
-                const float u0 = __uint_as_float(v[16 + 2 * j]), u1 = __uint_as_float(v[16 + 2 * j + 1]);
+                const float g0 = rst.x * __uint_as_float(v[2 * j]), g1 = rst.x * __uint_as_float(v[2 * j + 1]);
+                const float u0 = rst.x * __uint_as_float(v[16 + 2 * j]), u1 = rst.x * __uint_as_float(v[16 + 2 * j + 1]);
                 o[hh * 8 + j] = pack_bf16(silu(g0) * u0, silu(g1) * u1);
               }
             }
@@ -320,8 +324,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
               float rl[4], rh[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const float a = bf16_round(__uint_as_float(vl[4 * q + t]) + bls[t]);   // the projection output, bf16
-                const float bq = bf16_round(__uint_as_float(vh[4 * q + t]) + bhs[t]);
+                const float a = bf16_round(fmaf(rst.x, __uint_as_float(vl[4 * q + t]), bls[t]));   // the projection output, bf16
+                const float bq = bf16_round(fmaf(rst.x, __uint_as_float(vh[4 * q + t]), bhs[t]));
                 if (rot) {
                   rl[t] = bf16_round(bf16_round(a * cs[t]) + bf16_round(-bq * sn[t]));
                   rh[t] = bf16_round(bf16_round(bq * cs[t]) + bf16_round(a * sn[t]));
@@ -362,10 +366,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = make_float2(0.f, 0.f);
             }
-            tmem_ld_wait();
+            if (p.colsum) {  // mean term of a folded LayerNorm
+              const float2 nm = make_float2(rst.y, rst.y);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              f[j] = __fadd2_rn(f[j], make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+              for (int q = 0; q < 8; ++q) {
+                float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + q * 4 < p.N) cv = __ldg(reinterpret_cast<const float4*>(p.colsum + c0 + q * 4));
+                f[2 * q] = __ffma2_rn(nm, make_float2(cv.x, cv.y), f[2 * q]);
+                f[2 * q + 1] = __ffma2_rn(nm, make_float2(cv.z, cv.w), f[2 * q + 1]);
+              }
+            }
+            tmem_ld_wait();
+            {
+              const float2 rs2 = make_float2(rst.x, rst.x);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                f[j] = __ffma2_rn(rs2, make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), f[j]);
+            }
             if (p.act == ACT_GELU) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
@@ -585,6 +602,11 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     if (err) *err = "gemm: SwiGLU epilogue needs N % 64 == 0 and takes no residual";
     return -1;
   }
+  if ((a.row_stats || a.colsum) && (a.batches != 1 || !a.row_stats || (swiglu && a.colsum) ||
+                                    (reinterpret_cast<uintptr_t>(a.row_stats) & 7))) {
+    if (err) *err = "gemm: a folded norm needs row_stats, one row view, and no mean term with SwiGLU";
+    return -1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -687,6 +709,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.rope_sin = a.rope_sin;
   p.rope_cols = rope ? a.rope_cols : 0;
   p.rope_S = a.rope_S;
+  p.row_stats = reinterpret_cast<const float2*>(a.row_stats);
+  p.colsum = a.colsum;
 
   CUtensorMap mA, mB, mC;
   const uint64_t a_bs = a.batches > 1 ? static_cast<uint64_t>(a.a_batch_stride)

@@ -44,6 +44,13 @@ struct GemmArgs {
   const float* rope_sin = nullptr;
   int rope_cols = 0;
   int rope_S = 0;
+  // LayerNorm / RMSNorm of A folded into the GEMM: W already holds W * diag(norm weight) and `bias` holds
+  // bias + W @ norm_bias; the epilogue turns the raw product into the product of the NORMALISED rows,
+  //   acc <- rstd[r] * acc + (-mean[r] * rstd[r]) * colsum[n],
+  // with (rstd, -mean * rstd) per row from row_stats_launch() and colsum[n] = sum_k W'[n, k] (nullptr for RMSNorm,
+  // whose mean term is absent).  One row view only (batches == 1).
+  const float* row_stats = nullptr;  // [rows][2] fp32
+  const float* colsum = nullptr;     // [N] fp32
 };
 
 // Returns 0 on success, negative on error (message in *err if non-null).

@@ -114,6 +114,105 @@ norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long lon
   }
 }
 
+// ------------------------------------------------------------------ row statistics of a norm folded into the next GEMM
+// (rstd, -mean * rstd) per row; the GEMM that consumes the raw rows applies them in its epilogue (gemm.cuh: row_stats).
+// Read-only: half the traffic of norm_kernel, and nothing of the row has to stay in registers - each warp takes two
+// rows at a time to keep more loads in flight.
+template <bool RMS>
+__global__ void __launch_bounds__(256, 4)
+row_stats_kernel(const __nv_bfloat16* __restrict__ x, int rows, int dim, int ldx, float eps, float2* __restrict__ stats) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int r0 = warp * 2;
+  if (r0 >= rows) return;
+  const bool two = r0 + 1 < rows;
+  const __nv_bfloat16* xa = x + static_cast<long long>(r0) * ldx;
+  const __nv_bfloat16* xb = xa + (two ? ldx : 0);
+  const int nvec = dim >> 3;
+  uint4 ua[MAX_VEC_PER_LANE], ub[MAX_VEC_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      ua[i] = *reinterpret_cast<const uint4*>(xa + vi * 8);
+      ub[i] = *reinterpret_cast<const uint4*>(xb + vi * 8);
+    }
+  }
+  // same single-pass pivoted sums as norm_kernel
+  const float pa = RMS ? 0.f : __shfl_sync(0xffffffffu, unpack_bf16(ua[0].x).x, 0);
+  const float pb = RMS ? 0.f : __shfl_sync(0xffffffffu, unpack_bf16(ub[0].x).x, 0);
+  float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC_PER_LANE; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint32_t wa[4] = {ua[i].x, ua[i].y, ua[i].z, ua[i].w};
+      const uint32_t wb[4] = {ub[i].x, ub[i].y, ub[i].z, ub[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = unpack_bf16(wa[j]), fb = unpack_bf16(wb[j]);
+        const float d0 = fa.x - pa, d1 = fa.y - pa, e0 = fb.x - pb, e1 = fb.y - pb;
+        if (!RMS) {
+          a1 += d0 + d1;
+          b1 += e0 + e1;
+        }
+        a2 += d0 * d0 + d1 * d1;
+        b2 += e0 * e0 + e1 * e1;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    if (!RMS) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+    }
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+  }
+  if (lane < 2 && (lane == 0 || two)) {
+    const float s1 = lane ? b1 : a1, s2 = lane ? b2 : a2, pv = lane ? pb : pa;
+    float2 o;
+    if (RMS) {
+      o = make_float2(rsqrtf(s2 / dim + eps), 0.f);
+    } else {
+      const float m1 = s1 / dim;
+      const float rstd = rsqrtf(fmaxf(s2 / dim - m1 * m1, 0.f) + eps);
+      o = make_float2(rstd, -(pv + m1) * rstd);
+    }
+    stats[r0 + lane] = o;
+  }
+}
+
+// One-time weight fold (engine finalize): W[n, k] <- bf16(W[n, k] * g[k]); bias[n] += sum_k W[n, k] * b[k];
+// colsum[n] = sum_k W'[n, k] (of the ROUNDED products - what the tensor cores will multiply).  One warp per row n.
+__global__ void fold_norm_kernel(__nv_bfloat16* __restrict__ W, int N, int K, int ldw, const float* __restrict__ g,
+                                 const float* __restrict__ b, float* __restrict__ bias, float* __restrict__ colsum) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  __nv_bfloat16* w = W + static_cast<long long>(n) * ldw;
+  float su = 0.f, sv = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wf = __bfloat162float(w[k]);
+    if (b) sv += wf * b[k];
+    const __nv_bfloat16 wr = __float2bfloat16_rn(wf * g[k]);
+    w[k] = wr;
+    su += __bfloat162float(wr);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+  }
+  if (lane == 0) {
+    if (colsum) colsum[n] = su;
+    if (bias && b) bias[n] += sv;
+  }
+}
+
 // ------------------------------------------------------------------ RoPE (HF Qwen2, rotate_half)
 __global__ void rope_table_kernel(float* cos_t, float* sin_t, int S, int half, float theta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,6 +482,28 @@ int rmsnorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const flo
   }
   const int blocks = (rows + 7) / 8;
   launch_kernel(norm_kernel<true>, dim3(blocks), dim3(256), 0, s, x, rows, 1, 0, dim, ldx, w, nullptr, eps, y, 0, ldy);
+  return check_launch(err);
+}
+
+int row_stats_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, int rms, float eps, float* stats,
+                     cudaStream_t s, const char** err) {
+  if ((dim & 7) || dim > MAX_VEC_PER_LANE * 256 || (ldx & 7) || (reinterpret_cast<uintptr_t>(stats) & 7)) {
+    if (err) *err = "row_stats: dim must be a multiple of 8 and <= 1280";
+    return -1;
+  }
+  const int blocks = (rows + 15) / 16;  // 8 warps x 2 rows
+  if (rms) launch_kernel(row_stats_kernel<true>, dim3(blocks), dim3(256), 0, s, x, rows, dim, ldx, eps, reinterpret_cast<float2*>(stats));
+  else launch_kernel(row_stats_kernel<false>, dim3(blocks), dim3(256), 0, s, x, rows, dim, ldx, eps, reinterpret_cast<float2*>(stats));
+  return check_launch(err);
+}
+
+int fold_norm_launch(__nv_bfloat16* W, int N, int K, int ldw, const float* g, const float* b, float* bias,
+                     float* colsum, cudaStream_t s, const char** err) {
+  if (!W || !g || (b && !bias)) {
+    if (err) *err = "fold_norm: a norm bias needs a GEMM bias to fold into";
+    return -1;
+  }
+  fold_norm_kernel<<<(N + 7) / 8, 256, 0, s>>>(W, N, K, ldw, g, b, bias, colsum);
   return check_launch(err);
 }
 

@@ -18,6 +18,12 @@ int layernorm_launch_3d(const __nv_bfloat16* x, int rows, int batches, long long
                         cudaStream_t s, const char** err);
 
 // Qwen2RMSNorm (transformers Qwen2RMSNorm.forward): bf16(x * rsqrt(mean x^2 + eps)) * w.
+// Norm folded into the next GEMM (gemm.cuh: GemmArgs::row_stats): per-row (rstd, -mean * rstd) of x, and the
+// one-time fold of the norm's weight / bias into that GEMM's W / bias (+ the column sums its epilogue needs).
+int row_stats_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, int rms, float eps, float* stats,
+                     cudaStream_t s, const char** err);
+int fold_norm_launch(__nv_bfloat16* W, int N, int K, int ldw, const float* g, const float* b, float* bias,
+                     float* colsum, cudaStream_t s, const char** err);
 int rmsnorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const float* w, float eps,
                    __nv_bfloat16* y, int ldy, cudaStream_t s, const char** err);
 

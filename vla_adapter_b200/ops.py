@@ -76,6 +76,28 @@ def rmsnorm(x, w, eps=1e-6):
     return y
 
 
+def norm_linear(x, norm_w, norm_b, W, bias, eps=1e-6, act="none"):
+    """act(Linear(Norm(x))) the way the engine runs it: the norm's weight / bias are folded into (copies of) W / bias
+    and the GEMM consumes the raw rows; norm_b=None selects RMSNorm.  Returns (rows, N), or (rows, N/2) for swiglu."""
+    _need_cuda(x, norm_w, W)
+    rows, K = x.shape
+    N = W.shape[0]
+    rms = norm_b is None
+    Wf = W.clone()
+    bf = bias.clone() if bias is not None else (None if rms else torch.zeros(N, dtype=torch.float32, device=x.device))
+    colsum = torch.empty(N, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.vla_op_fold_norm(_ptr(Wf), N, K, Wf.stride(0), _ptr(norm_w), None if rms else _ptr(norm_b),
+                                    None if bf is None else _ptr(bf), _ptr(colsum), _stream()))
+    code = ACT[act]
+    out = torch.empty((rows, N // 2 if act == "swiglu" else N), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty(2 * rows, dtype=torch.float32, device=x.device)
+    _lib.check(lib.vla_op_norm_gemm(_ptr(x), rows, x.stride(0), _ptr(Wf), Wf.stride(0), N, K, _ptr(out), out.stride(0),
+                                    None if bf is None else _ptr(bf), _ptr(colsum), int(rms), eps, code, _ptr(stats),
+                                    _stream()))
+    return out
+
+
 def attention(qkv, B, S, n_heads, n_kv_heads, hd, causal):
     """qkv: (B*S, (n_heads + 2*n_kv_heads) * hd) packed [q | k | v]."""
     _need_cuda(qkv)
