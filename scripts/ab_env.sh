@@ -4,7 +4,7 @@ VAR=$1; R=${2:-2}
 for i in $(seq $R); do
   for v in "" 1; do
     if [ -z "$v" ]; then unset $VAR; else export $VAR=$v; fi
-    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --latency-iters 0 2>/dev/null | python -c "
+    timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --latency-iters 0 2>/dev/null | python -c "
 import json,sys,os
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 s=d['segments']

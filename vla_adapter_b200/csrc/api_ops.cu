@@ -129,12 +129,17 @@ int vla_op_gemm_rope(const void* A, int lda, int rows, const void* W, int ldw, i
   g.C = static_cast<__nv_bfloat16*>(C);
   g.ldc = ldc;
   g.bias = bias;
-  g.rope_cos = cos_t;
-  g.rope_sin = sin_t;
   g.rope_cols = rope_cols;
   g.rope_S = S;
   const char* err = nullptr;
-  int rc = vla::gemm_launch(g, static_cast<cudaStream_t>(stream), &err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!cos_t || !sin_t || S <= 0) return fail(-1, "gemm_rope: cos/sin tables required");
+  uint32_t* cs = nullptr;  // the epilogue reads the table transposed and packed
+  if (cudaMallocAsync(&cs, sizeof(uint32_t) * 32 * S, s) != cudaSuccess) return fail(-4, "gemm_rope: cudaMallocAsync failed");
+  int rc = vla::rope_pack_launch(cos_t, sin_t, S, cs, s, &err);
+  g.rope_cs = cs;
+  if (!rc) rc = vla::gemm_launch(g, s, &err);
+  cudaFreeAsync(cs, s);
   return rc ? fail(rc, err) : 0;
 }
 

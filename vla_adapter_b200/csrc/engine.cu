@@ -99,6 +99,7 @@ struct vla_engine {
   std::vector<LlmLayer> llm;
   float* llm_norm;
   float *rope_cos = nullptr, *rope_sin = nullptr;
+  uint32_t* rope_cs = nullptr;  // the same table transposed and packed for the GEMM's RoPE epilogue
   // head
   std::vector<HeadBlock> head;
   bf16 *x0, *head_fc2_w, *pp_w1, *pp_w2;
@@ -455,14 +456,17 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     }
     g.lda = D_LLM; g.rows = M; g.W = w.wqkv; g.ldw = D_LLM; g.N = QKV_LLM; g.K = D_LLM;
     g.C = e->l_qkv; g.ldc = QKV_LLM; g.bias = w.bqkv;
-    // Small batch: RoPE of the q and k heads rides in this GEMM's epilogue (one kernel less on the critical path).
-    // At bs=64 the rotation makes the epilogue the pacing stage (measured 148 us fused against 66 + 40 us), so the
-    // stand-alone bandwidth-bound kernel is used.
-    if (small) {
-      g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_cols = (HQ + HKV) * 64; g.rope_S = S;
+    // Small batch: RoPE of the q and k heads rides in this GEMM's epilogue (one kernel less on the critical path); the
+    // row's cos/sin pairs come from the transposed packed table, one coalesced load per frequency and tile.  At bs=64
+    // the fused form and GEMM + stand-alone kernel measure the same (prefill 28.5 ms either way), so the large-batch
+    // path keeps the two kernels; VLA_ROPE_FUSE=1 fuses at every batch size.
+    static const bool rope_fuse_all = getenv("VLA_ROPE_FUSE") != nullptr;
+    const bool fuse_rope = small || rope_fuse_all;
+    if (fuse_rope) {
+      g.rope_cs = e->rope_cs; g.rope_ld = e->maxS; g.rope_cols = (HQ + HKV) * 64; g.rope_S = S;
     }
     CK(vla::gemm_launch(g, s, &_err));
-    if (!small) CK(vla::rope_apply_launch(e->l_qkv, QKV_LLM, 0, HQ + HKV, B, S, e->rope_cos, e->rope_sin, s, &_err));
+    if (!fuse_rope) CK(vla::rope_apply_launch(e->l_qkv, QKV_LLM, 0, HQ + HKV, B, S, e->rope_cos, e->rope_sin, s, &_err));
     CK(vla::attention_launch(e->l_qkv, QKV_LLM, 0, HQ * 64, (HQ + HKV) * 64, B, S, HQ, HQ / HKV, 64, e->cfg.causal,
                              e->l_attn, D_LLM, s, &_err));
     g = vla::GemmArgs();
@@ -869,6 +873,8 @@ int vla_finalize(vla_engine* e) {
     e->rope_sin = e->dalloc<float>(static_cast<size_t>(S) * 32);
     const char* err = nullptr;
     int rc = vla::rope_table_launch(e->rope_cos, e->rope_sin, S, 32, ROPE_THETA, 0, &err);
+    e->rope_cs = e->dalloc<uint32_t>(static_cast<size_t>(S) * 32);
+    if (!rc) rc = vla::rope_pack_launch(e->rope_cos, e->rope_sin, S, e->rope_cs, 0, &err);
     if (rc) return e->fail(rc, err ? err : "rope table failed");
     const int max_pos = e->NP > 65 ? e->NP : 65;
     e->prope_cos = e->dalloc<float>(static_cast<size_t>(max_pos) * 112);

@@ -53,9 +53,8 @@ struct GemmDev {
   const __nv_bfloat16* resid;
   long long r_bs;
   int ldr;
-  const float* rope_cos;  // RoPE fused into the epilogue (see GemmArgs)
-  const float* rope_sin;
-  int rope_cols, rope_S;
+  const uint32_t* rope_cs;  // RoPE fused into the epilogue (see GemmArgs)
+  int rope_cols, rope_S, rope_ld;
   const float2* row_stats;  // normalisation of A folded into the epilogue (see GemmArgs)
   const float* colsum;
 };
@@ -293,9 +292,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
           }
         } else if (p.rope_cols > 0) {
           // q/k projection with RoPE: a 64-wide head = two 32-column chunks (lo, hi) of this warp; out_lo = lo*cos -
-          // hi*sin, out_hi = hi*cos + lo*sin, every product and sum rounded to bf16 like the eager reference
-          const int rr = r0 + lane;
-          const int pos = rr % p.rope_S;
+          // hi*sin, out_hi = hi*cos + lo*sin, every product and sum rounded to bf16 like the eager reference.
+          // This row's 32 (cos, sin) pairs are loaded once per tile (the same for every head).
+          uint32_t cs[32];
+          if (n0 < p.rope_cols) {
+            const uint32_t* tab = p.rope_cs + (r0 + lane) % p.rope_S;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs[j] = __ldg(tab + j * p.rope_ld);
+          }
 #pragma unroll 1
           for (int ch = 0; ch < wcols; ch += 64) {
             const int c0 = n0 + ch;
@@ -314,21 +318,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 if (c0 + 32 + q * 4 < p.N) bh = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 32 + q * 4));
               }
               const float bls[4] = {bl.x, bl.y, bl.z, bl.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w};
-              float cs[4] = {1.f, 1.f, 1.f, 1.f}, sn[4] = {0.f, 0.f, 0.f, 0.f};
-              if (rot) {
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.rope_cos + pos * 32 + q * 4));
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.rope_sin + pos * 32 + q * 4));
-                cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
-                sn[0] = s4.x; sn[1] = s4.y; sn[2] = s4.z; sn[3] = s4.w;
-              }
               float rl[4], rh[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float a = bf16_round(fmaf(rst.x, __uint_as_float(vl[4 * q + t]), bls[t]));   // the projection output, bf16
                 const float bq = bf16_round(fmaf(rst.x, __uint_as_float(vh[4 * q + t]), bhs[t]));
                 if (rot) {
-                  rl[t] = bf16_round(bf16_round(a * cs[t]) + bf16_round(-bq * sn[t]));
-                  rh[t] = bf16_round(bf16_round(bq * cs[t]) + bf16_round(a * sn[t]));
+                  const float cc = __uint_as_float(cs[4 * q + t] << 16), sn = __uint_as_float(cs[4 * q + t] & 0xffff0000u);
+                  rl[t] = bf16_round(bf16_round(a * cc) + bf16_round(-bq * sn));
+                  rh[t] = bf16_round(bf16_round(bq * cc) + bf16_round(a * sn));
                 } else {
                   rl[t] = a;
                   rh[t] = bq;
@@ -662,7 +660,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   if (swiglu && (bn & 127)) bn = 128;
   const bool rope = a.rope_cols > 0;
   if (rope) {
-    if (!a.rope_cos || !a.rope_sin || a.rope_S <= 0 || (a.rope_cols & 63) || (a.N & 63) || a.rope_cols > a.N || swiglu ||
+    if (!a.rope_cs || a.colsum || a.rope_S <= 0 || (a.rope_cols & 63) || (a.N & 63) || a.rope_cols > a.N || swiglu ||
         a.act != ACT_NONE || a.colscale || a.resid || a.batches != 1) {
       if (err) *err = "gemm: fused RoPE needs plain bias epilogue, one row view, N and rope_cols multiples of 64";
       return -1;
@@ -705,10 +703,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.resid = fused_resid ? a.resid : nullptr;
   p.r_bs = a.batches > 1 ? a.r_batch_stride : 0;
   p.ldr = a.ldr;
-  p.rope_cos = a.rope_cos;
-  p.rope_sin = a.rope_sin;
+  p.rope_cs = a.rope_cs;
   p.rope_cols = rope ? a.rope_cols : 0;
   p.rope_S = a.rope_S;
+  p.rope_ld = a.rope_ld > 0 ? a.rope_ld : a.rope_S;
   p.row_stats = reinterpret_cast<const float2*>(a.row_stats);
   p.colsum = a.colsum;
 

@@ -39,9 +39,11 @@ struct GemmArgs {
   int act = ACT_NONE;
   int force_bn = 0;  // 0 = heuristic, else 64/128/256
   // HF rotate_half RoPE fused into the epilogue (Qwen2 q/k projection): output columns [0, rope_cols) are heads of
-  // width 64 rotated with the cos/sin of position (row % rope_S); tables are [rope_S][32] fp32 holding bf16 values.
-  const float* rope_cos = nullptr;
-  const float* rope_sin = nullptr;
+  // width 64 rotated with the cos/sin of position (row % rope_S).  rope_cs is the table TRANSPOSED and packed,
+  // [32][rope_S] words of (bf16 cos | bf16 sin << 16) (rope_pack_launch): the 32 lanes of an epilogue warp are 32
+  // consecutive rows = positions, so one load instruction reads one line.
+  const uint32_t* rope_cs = nullptr;
+  int rope_ld = 0;  // positions per table row (>= rope_S; 0 = rope_S)
   int rope_cols = 0;
   int rope_S = 0;
   // LayerNorm / RMSNorm of A folded into the GEMM: W already holds W * diag(norm weight) and `bias` holds

@@ -213,6 +213,17 @@ __global__ void fold_norm_kernel(__nv_bfloat16* __restrict__ W, int N, int K, in
   }
 }
 
+// [S][32] fp32 cos / sin tables (bf16 values) -> [32][S] words (bf16 cos | bf16 sin << 16) for the GEMM's RoPE epilogue
+__global__ void rope_pack_kernel(const float* __restrict__ cos_t, const float* __restrict__ sin_t, int S,
+                                 uint32_t* __restrict__ cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * 32) return;
+  const int j = i / S, pos = i - j * S;
+  const uint32_t c = __float_as_uint(bf16_round(cos_t[pos * 32 + j])) >> 16;
+  const uint32_t sn = __float_as_uint(bf16_round(sin_t[pos * 32 + j])) & 0xffff0000u;
+  cs[i] = c | sn;
+}
+
 // ------------------------------------------------------------------ RoPE (HF Qwen2, rotate_half)
 __global__ void rope_table_kernel(float* cos_t, float* sin_t, int S, int half, float theta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -504,6 +515,11 @@ int fold_norm_launch(__nv_bfloat16* W, int N, int K, int ldw, const float* g, co
     return -1;
   }
   fold_norm_kernel<<<(N + 7) / 8, 256, 0, s>>>(W, N, K, ldw, g, b, bias, colsum);
+  return check_launch(err);
+}
+
+int rope_pack_launch(const float* cos_t, const float* sin_t, int S, uint32_t* cs, cudaStream_t s, const char** err) {
+  rope_pack_kernel<<<(S * 32 + 255) / 256, 256, 0, s>>>(cos_t, sin_t, S, cs);
   return check_launch(err);
 }
 

@@ -28,6 +28,8 @@ int rmsnorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const flo
                    __nv_bfloat16* y, int ldy, cudaStream_t s, const char** err);
 
 // cos/sin tables (fp32 values already rounded to bf16), [S][half] each; inv_freq_j = theta^(-2j/(2*half)).
+// [S][32] fp32 tables -> the transposed packed table of the GEMM's RoPE epilogue (gemm.cuh: GemmArgs::rope_cs)
+int rope_pack_launch(const float* cos_t, const float* sin_t, int S, uint32_t* cs, cudaStream_t s, const char** err);
 int rope_table_launch(float* cos_t, float* sin_t, int S, int half, float theta, cudaStream_t s,
                       const char** err);
 // HF rotate_half RoPE, in place, width-64 heads: out = bf16(bf16(x*cos) + bf16(rot(x)*sin)).
