@@ -68,6 +68,30 @@ def test_engine_matches_oracle(pro, n_images, B, L):
 
 
 @pytest.mark.parametrize("pro", [False, True])
+def test_engine_matches_oracle_full_depth(pro):
+    """The same gate on the FULL-DEPTH architecture (DINOv2 24 / SigLIP 27 blocks with the block-(depth-2) tap, 24 LLM
+    layers, 24 policy blocks, 2 images, L=48 - BASELINE.json's model; only the embedding table is cut to 2048 rows)."""
+    cfg, truth, ref16, normalized, actions, ha, got, launches = _run_case(pro, 2, 2, 48, dino_depth=24, siglip_depth=27,
+                                                                          seed=4)
+    report = []
+    for k in TAPS:
+        t = truth[k].float().reshape(-1)
+        r = _rel(ref16[k].reshape(-1), t)
+        g = _rel(got[k].float(), t)
+        report.append(f"{k}: engine {g:.4f} ref_bf16 {r:.4f}")
+    print("\n".join(report))
+    for line, k in zip(report, TAPS):
+        t = truth[k].float().reshape(-1)
+        assert _rel(got[k].float(), t) <= max(2 * _rel(ref16[k].reshape(-1), t), 1e-2), "\n".join(report)
+    tn = truth["normalized"].numpy()
+    e_ref = np.abs(ref16["normalized"].numpy() - tn)
+    e_eng = np.abs(normalized - tn)
+    print(f"actions: engine max {e_eng.max():.4f} mean {e_eng.mean():.4f} | ref_bf16 max {e_ref.max():.4f} mean {e_ref.mean():.4f}")
+    assert e_eng.max() <= max(2 * e_ref.max(), 2e-2)
+    assert e_eng.mean() <= 5e-3 + e_ref.mean()
+
+
+@pytest.mark.parametrize("pro", [False, True])
 def test_engine_aloha_shaped_chunk(pro):
     """The larger-chunk preset of the reference (ALOHA constants, prismatic/vla/constants.py:42-47: 25 x 14 chunk,
     14-d proprio; fc1 input 14*896) - BASELINE.json configs[4] asks for the Pro head at a larger action chunk."""
