@@ -128,6 +128,11 @@ def synth_inputs(B: int, L: int, seed: int, device):
     return pix.to(torch.bfloat16).contiguous(), ids, prop.float().contiguous()
 
 
+def workload_name(B: int, L: int, variant: str) -> str:
+    return (f"LIBERO predict_action bs={B}/GPU (BASELINE.json configs[2]): 2x224px images, "
+            f"L={L} prompt, 64 ActionQuery, proprio, {T_CHUNK}x{A_DIM} chunk, {variant} head")
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm (oracle port, bf16 like the reference requires) on all host
     cores.  Each step is a bounded sample of the step's batch: ONE observation (1/B of the batch)."""
@@ -161,8 +166,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"LIBERO predict_action bs={args.batch} (configs[2]); reference arm samples 1 observation/step",
-                   "n_images": N_IMAGES, "prompt_len": PROMPT_LEN, "chunk": [T_CHUNK, A_DIM], "variant": args.variant},
+        # the same workload as our arm; this arm times a bounded sample of it (one observation per step, see `sample`)
+        "config": {"workload": workload_name(args.batch, PROMPT_LEN, args.variant), "global_batch": args.gpus * args.batch,
+                   "per_gpu_batch": args.batch, "sampled_observations_per_step": 1},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -384,8 +390,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"LIBERO predict_action bs={B}/GPU (BASELINE.json configs[2]): 2x224px images, "
-                                   f"L={L} prompt, 64 ActionQuery, proprio, {T_CHUNK}x{A_DIM} chunk, {args.variant} head",
+            "config": {"workload": workload_name(B, L, args.variant),
                        "global_batch": world * B, "per_gpu_batch": B, "params": n_params,
                        "parallelism": f"sample-sharded x{world}, full weight replica per GPU, all-gather of chunks",
                        "l2": "no explicit flush: per-step working set (2.7 GB weights + >4 GB activations) >> 126 MB L2"},
