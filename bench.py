@@ -27,6 +27,14 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+_T0 = time.perf_counter()
+
+
+def stage(msg: str) -> None:
+    """Progress on stderr (rank 0): if a run is cut short the log says which stage it was in."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
 METRIC = "action_chunks_per_sec"
 UNIT = "chunks/s"
 PROMPT_LEN = 48
@@ -208,7 +216,11 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        stage(f"init_process_group(nccl), world {world}")
         dist.init_process_group("nccl", device_id=dev)
+        stage("process group up")
 
     from vla_adapter_b200 import _lib
     from vla_adapter_b200.engine import VLAEngine
@@ -223,6 +235,7 @@ def main():
                                                          "mask": [True] * (A_DIM - 1) + [False]}}})
     n_params = load_random_weights(eng, seed=0, n_images=N_IMAGES, action_dim=A_DIM, proprio_dim=P_DIM, pro=pro)
     eng.finalize()
+    stage("engine built: random weights loaded, finalized")
     lib = _lib.load()
 
     pix, ids, prop = synth_inputs(B, L, seed=rank, device=dev)
@@ -250,6 +263,7 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident throughput
+    stage("warm-up + timed steps (device-resident inputs)")
     for _ in range(Wu):
         step_device()
     sync_all()
@@ -269,6 +283,7 @@ def main():
     assert torch.isfinite(out).all(), "non-finite action chunk"
 
     # ---------------- end to end through the host-buffer C-ABI call (pinned host memory)
+    stage("end-to-end steps through the host-buffer call")
     pix_h, ext_h, aq_h, prop_h = pix.cpu().pin_memory(), ext.pin_memory(), aq.pin_memory(), prop.cpu().pin_memory()
     on_h = torch.empty((B, T_CHUNK, A_DIM), dtype=torch.float32).pin_memory()
     ou_h = torch.empty((B, T_CHUNK, A_DIM), dtype=torch.float32).pin_memory()
@@ -302,6 +317,7 @@ def main():
     h2d_u8 = img_h.numel() + ext_h.numel() * 8 + aq_h.numel() * 4 + prop_h.numel() * 4
 
     # ---------------- roofline of the dominant kernel: tcgen05 GEMM, timed per launch with CUDA events
+    stage("per-launch GEMM timing + segment timing")
     lib.vla_profile_gemm(1)
     step_device()
     torch.cuda.synchronize()
@@ -348,6 +364,7 @@ def main():
                      "note": "whole step (all kernels) against the same measured dense-bf16 peak"}
 
     # ---------------- bs=1 latency through the host path (p50 / p90), BASELINE.json's second metric
+    stage("bs=1 latency")
     lat = []
     one = [t[:1].contiguous().pin_memory() for t in (pix_h, ext_h, aq_h, prop_h)]
     o1, o2 = on_h[:1].clone().pin_memory(), ou_h[:1].clone().pin_memory()
@@ -364,6 +381,7 @@ def main():
                    "how": "wall clock around vla_predict_host(B=1) incl. H2D/D2H and stream sync"}
 
     # ---------------- CPU baseline (rank 0, N=1 only): the oracle on this box's cores, bounded sample
+    stage("CPU baseline (oracle)")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import vla_oracle as O
