@@ -216,10 +216,20 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         stage(f"init_process_group(nccl), world {world}")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the one JSON line only: whatever NCCL prints while the communicator comes up (its
+        # "NCCL version ..." line when NCCL_DEBUG is set) is sent to stderr by pointing fd 1 at fd 2 meanwhile
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         stage("process group up")
 
     from vla_adapter_b200 import _lib
