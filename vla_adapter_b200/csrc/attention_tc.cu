@@ -183,7 +183,6 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
   uint32_t v[NLIVE > 0 ? NLIVE : 1][32];
   float mloc = -INFINITY;
   if (NLIVE > 0) {
-#pragma unroll
     if (p.debug & 64) {  // timing experiment: no TMEM loads
 #pragma unroll
       for (int c = 0; c < NLIVE; ++c)
