@@ -14,6 +14,8 @@ timed on this box's cores on a bounded sample.
 from __future__ import annotations
 
 import argparse
+import datetime
+import faulthandler
 import json
 import os
 import statistics
@@ -28,12 +30,34 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 _T0 = time.perf_counter()
+_RANK = int(os.environ.get("RANK", "0"))
+STAGE_LIMIT_S = 240  # no single stage of the bench takes longer; a stage that does is a hang
+
+# stdout carries exactly ONE line, the JSON result.  Anything a library prints to fd 1 (NCCL's banner when NCCL_DEBUG is
+# set, a stray print) goes to stderr for the whole run; the result line is written to the saved descriptor.
+_RESULT_FD = None
+
+
+def claim_stdout() -> None:
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_result(line: dict) -> None:
+    claim_stdout()
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
 
 def stage(msg: str) -> None:
-    """Progress on stderr (rank 0): if a run is cut short the log says which stage it was in."""
-    if int(os.environ.get("RANK", "0")) == 0:
-        print(f"[bench +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+    """Progress of EVERY rank on stderr, and a per-stage dead-man switch: if a rank sits in one stage for more than
+    STAGE_LIMIT_S its Python stack is dumped and the process exits non-zero - a hang costs minutes and names its
+    stage and rank instead of running into the launcher's limit."""
+    print(f"[bench r{_RANK} +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+    faulthandler.cancel_dump_traceback_later()
+    faulthandler.dump_traceback_later(STAGE_LIMIT_S, exit=True, file=sys.stderr)
 
 METRIC = "action_chunks_per_sec"
 UNIT = "chunks/s"
@@ -181,7 +205,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 def main():
@@ -198,6 +222,7 @@ def main():
     ap.add_argument("--chunk", default="8x7x8", help="chunk_len x action_dim x proprio_dim: 8x7x8 = LIBERO / CALVIN "
                     "(constants.py:28-40), 25x14x14 = the reference's larger-chunk preset (ALOHA, constants.py:42-47)")
     args = ap.parse_args()
+    claim_stdout()
     global T_CHUNK, A_DIM, P_DIM
     T_CHUNK, A_DIM, P_DIM = (int(v) for v in args.chunk.split("x"))
     if args.warmup < 3 and args.impl == "ours":
@@ -217,25 +242,22 @@ def main():
     if world > 1:
         import torch.distributed as dist
         stage(f"init_process_group(nccl), world {world}")
-        # stdout carries the one JSON line only: whatever NCCL prints while the communicator comes up (its
-        # "NCCL version ..." line when NCCL_DEBUG is set) is sent to stderr by pointing fd 1 at fd 2 meanwhile
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        # a collective that does not complete within two minutes is a failure, not something to wait 10 minutes for
+        # (the reference sets an explicit process-group timeout too, vla-scripts/evaluate_calvin.py:877); the flight
+        # recorder then says which collective of which rank was outstanding
+        os.environ.setdefault("TORCH_NCCL_TRACE_BUFFER_SIZE", "2000")
+        os.environ.setdefault("TORCH_NCCL_DUMP_ON_TIMEOUT", "1")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+        dist.barrier()
+        torch.cuda.synchronize()
         stage("process group up")
 
     from vla_adapter_b200 import _lib
     from vla_adapter_b200.engine import VLAEngine
     from vla_adapter_b200.weights import load_random_weights
     from vla_adapter_b200 import tokens
+    from vla_adapter_b200 import sharding
 
     B, L, K, Wu = args.batch, PROMPT_LEN, args.steps, args.warmup
     pro = args.variant == "pro"
@@ -251,12 +273,12 @@ def main():
     pix, ids, prop = synth_inputs(B, L, seed=rank, device=dev)
     ext, _, _, aq, _ = tokens.build(ids.cpu(), None, A_DIM)
     ext_d, aq_d = ext.to(dev), aq.to(dev)
-    gathered = torch.empty((world * B, T_CHUNK, A_DIM), dtype=torch.float32, device=dev) if world > 1 else None
 
     def step_device():
         out_n, out_u, _ = eng.predict_device(pix, ext_d, aq_d, prop)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out_u)  # the only collective: action chunks over NVLink
+            # the only collective of the path: the product's own gather of action chunks over NVLink
+            sharding.gather_chunks(out_u, world * B)
         return out_u
 
     def sync_all():
@@ -304,7 +326,7 @@ def main():
     for _ in range(K):
         eng.predict_host(pix_h, ext_h, aq_h, prop_h, on_h, ou_h)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, ou_h.to(dev, non_blocking=True))
+            sharding.gather_chunks(ou_h.to(dev, non_blocking=True), world * B)
     e1.record()
     sync_all()
     ms_e2e = reduce_max(e0.elapsed_time(e1) / K)
@@ -433,11 +455,13 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit_result(line)
+    stage("done")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
+    faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == "__main__":

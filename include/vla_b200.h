@@ -138,6 +138,13 @@ int vla_segment_times(vla_engine* e, float* ms3);
  * "head_x.<i>" policy state after block i (B,T,896).  Returns the number of bytes through *bytes. */
 int vla_get_tap(vla_engine* e, const char* name, void* dst, size_t capacity, size_t* bytes);
 
+/* The device-pointer calls (vla_predict, vla_predict_u8) only ENQUEUE work, like the reference's CUDA calls behind
+ * predict_action before its .cpu() at MP:872: what the kernels find out (a token id outside the vocabulary - the
+ * reference's embedding lookup would raise a device assert - or a bad ActionQuery index) is reported by this call,
+ * which waits for `stream`, returns VLA_ERR_INVALID / VLA_ERR_CUDA accordingly and clears the flag.  The offending
+ * row of the LLM input is zero-filled, never left stale.  vla_predict_host* perform this check themselves. */
+int vla_check_errors(vla_engine* e, void* stream);
+
 /* Kernel launches issued by this engine's last vla_predict call (own kernels only). */
 long long vla_last_launch_count(const vla_engine* e);
 
@@ -214,6 +221,18 @@ int vla_profile_gemm_read(double* total_ms, long long* launches);
 
 const char* vla_global_error(void);
 long long vla_total_launch_count(void);
+
+/* Device watchdog.  Every mbarrier wait inside the tcgen05 kernels is bounded (default 10 s; VLA_WATCHDOG_MS or
+ * vla_watchdog_set_timeout_ms override): on timeout the waiting warp records (kernel, role, barrier, parity, CTA,
+ * thread, SM) in a host-mapped buffer and traps, so a protocol deadlock ends as VLA_ERR_CUDA with a message that names
+ * the barrier instead of a hung process (the reference relies on torch.distributed's timeout for the same purpose,
+ * vla-scripts/evaluate_calvin.py:877).  vla_watchdog_report copies the records so far (text, NUL-terminated, truncated
+ * to `capacity`) and returns the full length (0 = none); vla_watchdog_selftest launches a kernel that deadlocks on
+ * purpose and returns VLA_ERR_CUDA once the watchdog has fired (the CUDA context is unusable afterwards: tests run
+ * it in a child process). */
+int vla_watchdog_report(char* buf, size_t capacity);
+int vla_watchdog_set_timeout_ms(int ms);
+int vla_watchdog_selftest(void* stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,10 @@ SIGNATURES = {
     "vla_op_rope": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vla_profile_gemm": (c_int, [c_int]),
     "vla_profile_gemm_read": (c_int, [C.POINTER(C.c_double), C.POINTER(c_ll)]),
+    "vla_check_errors": (c_int, [c_void_p, c_void_p]),
+    "vla_watchdog_report": (c_int, [C.c_char_p, C.c_size_t]),
+    "vla_watchdog_set_timeout_ms": (c_int, [c_int]),
+    "vla_watchdog_selftest": (c_int, [c_void_p]),
     "vla_global_error": (C.c_char_p, []),
     "vla_total_launch_count": (c_ll, []),
 }
@@ -106,6 +110,10 @@ def check(rc: int, engine=None) -> None:
     lib = load()
     msg = (lib.vla_last_error(engine) if engine else lib.vla_global_error()) or b""
     msg = msg.decode("utf-8", "replace")
+    if rc == -4:  # CUDA error: if the device watchdog fired, its records say which barrier was stuck
+        buf = C.create_string_buffer(4096)
+        if lib.vla_watchdog_report(buf, 4096) > 0 and buf.value.decode("utf-8", "replace") not in msg:
+            msg += "\n" + buf.value.decode("utf-8", "replace")
     if rc in (-1, -2, -3):
         raise ValueError(f"libvla_b200: {msg} (status {rc})")
     raise RuntimeError(f"libvla_b200: {msg} (status {rc})")

@@ -9,6 +9,8 @@
 #include "launch.cuh"
 #include "ops.cuh"
 
+#include <cstdio>
+
 namespace vla {
 
 namespace {
@@ -439,7 +441,8 @@ int launch_splitkv(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16
   constexpr int SMEM_TILES = (16 + 4 * 4 * SK_BN) * LDS * 2;
   constexpr int SMEM_MERGE = 16 * LDS * 2 + (128 + 4 * 16 * HDP) * 4;
   constexpr int SMEM = SMEM_TILES > SMEM_MERGE ? SMEM_TILES : SMEM_MERGE;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;  // the shared-memory opt-in is per device
+  bool& attr_set = attr_flag.here();
   if (!attr_set) {
     if (cudaFuncSetAttribute(splitkv_attn_kernel<HD, HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
         cudaSuccess) {
@@ -467,7 +470,8 @@ int launch_attn(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k
                 const char** err) {
   constexpr int LDS = HDP + 8;
   constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * LDS * 2;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;  // the shared-memory opt-in is per device
+  bool& attr_set = attr_flag.here();
   if (!attr_set) {
     if (cudaFuncSetAttribute(flash_attn_kernel<HD, HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
         cudaSuccess) {
@@ -536,6 +540,19 @@ int cross_attention_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_
     }
     const int rc = attention_tc_launch(q, ld_q, Sq, k, v, ld_kv, Skv, B, n_heads, group, hd, causal, out, ld_out, Sq, s, err);
     if (rc <= 0) return rc;
+    // The shape is outside what the tensor-core kernel serves (work-item table, alignment).  The mma.sync kernel below
+    // computes the same result ~2x slower; say so once instead of degrading silently - and refuse when the caller asked
+    // for the tensor-core kernel explicitly (vla_set_attention_impl(2)).
+    if (g_attn_impl == 2) {
+      if (err) *err = "attention: shape not served by the tcgen05 kernel (vla_set_attention_impl(2) forbids the mma.sync path)";
+      return -1;
+    }
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      fprintf(stderr, "libvla_b200: attention shape (Sq %d, Skv %d, heads %d, hd %d) runs on the slower mma.sync kernel\n",
+              Sq, Skv, n_heads, hd);
+    }
   }
   // few queries against many keys (the policy's Bridge-Attention): the warps split the keys instead of the queries
   if (!causal && Sq <= 32 && Skv >= 128 && g_attn_impl != 1 && !(ld_out & 1)) {

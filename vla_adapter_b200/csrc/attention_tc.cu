@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "launch.cuh"
 #include "ops.cuh"
+#include "watchdog.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -43,7 +44,7 @@ namespace {
 constexpr int FA_BM = 128;
 constexpr uint32_t FA_TILE_BYTES = 128 * 128;  // Q tile: 128 rows x 64 bf16
 constexpr uint32_t FA_TAIL_BYTES = 128 * 32;   // Q tail: 128 rows x 16 bf16
-constexpr int FA_MAX_ITEMS = 24;               // work items per (sample, kv head)
+constexpr int FA_MAX_ITEMS = 40;               // work items per (sample, kv head): 3 images, L <= 127 -> 8 x 7 units = 28 items
 
 struct FaDev {
   int Sq, Skv, group, kv_heads, causal;
@@ -179,7 +180,7 @@ template <int HD, int NLIVE, bool MASKED, bool SPLIT>
 VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint32_t tO, int k0h, int grow, int j, int half,
                                 float sl2, float& m_ref, float& l, float* xch_mine, const float* xch_other, int bar_id,
                                 uint32_t turn_wait, uint32_t turn_parity, uint32_t turn_arrive, uint32_t s_free_bar,
-                                uint32_t pv_done_bar, uint32_t pv_parity) {
+                                uint32_t pv_done_bar, uint32_t pv_parity, uint32_t my_note) {
   uint32_t v[NLIVE > 0 ? NLIVE : 1][32];
   float mloc = -INFINITY;
   if (NLIVE > 0) {
@@ -229,6 +230,7 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
     m_new = fmaxf(m_new, *xch_other);
   }
   if (pv_done_bar) {  // PV of the previous tile has retired: O is stable and the P columns may be rewritten
+    wd_note(my_note, VLA_WD_NOTE(9, 0, pv_parity, j));
     mbar_wait(pv_done_bar, pv_parity);
     tc_fence_after();
   }
@@ -257,7 +259,10 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
   }
   // The exponentials of the two slots take turns: while one slot owns the MUFU, the other's P -> PV -> next QK ->
   // TMEM load -> row max chain runs on the tensor pipe, instead of both slots doing each phase in lockstep.
-  if (turn_wait) mbar_wait(turn_wait, turn_parity);
+  if (turn_wait) {
+    wd_note(my_note, VLA_WD_NOTE(10, 0, turn_parity, j));
+    mbar_wait(turn_wait, turn_parity);
+  }
   if (NLIVE > 0) {
     const float mb = m_ref * sl2;
     const float2 sl2v = make_float2(sl2, sl2), nmb = make_float2(-mb, -mb);
@@ -319,7 +324,7 @@ struct FaSmem {
   static constexpr uint32_t OFF_KT = OFF_QT + QBUFS * FA_TAIL_BYTES;
   static constexpr uint32_t OFF_VT = OFF_KT + STAGES * KV_TAIL;
   static constexpr uint32_t OFF_BAR = TAIL ? OFF_VT + STAGES * KV_TAIL : OFF_QT;
-  static constexpr uint32_t OFF_XCH = OFF_BAR + 256;  // row-max / row-sum exchange: [slot][parity][half][128] floats
+  static constexpr uint32_t OFF_XCH = OFF_BAR + 384;  // row-max / row-sum exchange: [slot][parity][half][128] floats
   static constexpr uint32_t XCH_END = OFF_XCH + (SPLIT ? 2 * 2 * 2 * 128 * 4 : 0);
   // Head dim 64, 128-key tiles: the epilogue leaves through shared memory and one TMA store per warp (32 rows x 32
   // columns, 64B-swizzled, 2 KB per softmax warp) - the per-thread 16-byte row stores took ~3k cycles per item during
@@ -369,11 +374,17 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   auto kv_full = [&](int s) { return bar_base + 8u * (22 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (22 + NS + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_BAR + 8 * (22 + 2 * NS));
+  // watchdog (common.cuh): warp 3 is the monitor, parked on done_bar; every other warp arrives there at its end and
+  // leaves a note (which barrier, parity, step) before each wait
+  constexpr int N_WARPS = L::THREADS / 32;
+  const uint32_t done_bar = bar_base + 8u * (23 + 2 * NS);
+  const uint32_t note_base = bar_base + 8u * (24 + 2 * NS);
 
   // shfl-broadcast warp index: the role branches are then provably warp-uniform, so the MMA warp's descriptor
   // arithmetic stays on the uniform datapath and tcgen05.mma issues at the hardware rate (scripts/ubench/mma3.cu)
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t my_note = note_base + 4u * static_cast<uint32_t>(warp_idx);
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&mapQ);
@@ -396,6 +407,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 2);  // one release per slot's MMA warp
     }
+    mbar_init(done_bar, N_WARPS - 1);
     mbar_fence_init();
     fence_proxy_async();
   }
@@ -424,6 +436,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       for (int x = 0; x < 2; ++x) {
         if (!it.n[x]) continue;
         const int qb = x * 2 + static_cast<int>(q_cnt[x] & 1u);
+        wd_note(my_note, VLA_WD_NOTE(1, qb, ((q_cnt[x] >> 1) & 1u) ^ 1u, item));
         mbar_wait_relaxed(q_empty(qb), ((q_cnt[x] >> 1) & 1u) ^ 1u);
         ++q_cnt[x];
         if (elect_one()) {
@@ -438,6 +451,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const int s = static_cast<int>(kv_cnt % NS);
         const uint32_t ph = (kv_cnt / NS) & 1u;
         ++kv_cnt;
+        wd_note(my_note, VLA_WD_NOTE(2, s, ph ^ 1u, kv_cnt));
         mbar_wait_relaxed(kv_empty(s), ph ^ 1u);
         if (elect_one()) {
           fa_trace(p, 0, tr_cnt, 100 + j);
@@ -474,6 +488,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       auto need_kv = [&](int j) {
         while (kv_waited <= j) {
           const uint32_t c = kv0 + kv_waited;
+          wd_note(my_note, VLA_WD_NOTE(3, c % NS, (c / NS) & 1u, c));
           mbar_wait(kv_full(static_cast<int>(c % NS)), (c / NS) & 1u);
           ++kv_waited;
         }
@@ -528,6 +543,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       };
       if (n_x) {
         qbuf = x * 2 + static_cast<int>(q_cnt & 1u);
+        wd_note(my_note, VLA_WD_NOTE(4, qbuf, (q_cnt >> 1) & 1u, item));
         mbar_wait(q_full(qbuf), (q_cnt >> 1) & 1u);
         ++q_cnt;
         tc_fence_after();
@@ -537,15 +553,20 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         if (j < n_x) {
           if (L::DEALIAS) {
             // the next tile's scores as soon as this tile's have been read: S(j+1) is ready before softmax(j) ends
+            wd_note(my_note, VLA_WD_NOTE(5, x, f_cnt & 1u, f_cnt));
             mbar_wait(s_free(x), f_cnt & 1u);
             ++f_cnt;
             tc_fence_after();
             if (j + 1 < n_x && !(p.debug & 16)) issue_qk(j + 1);
           }
+          wd_note(my_note, VLA_WD_NOTE(6, x, p_cnt & 1u, p_cnt));
           mbar_wait(p_ready(x), p_cnt & 1u);
           if (lane == 0) fa_trace(p, 1, tr_cnt, 300 + x * 10 + j);
           ++p_cnt;
-          if (j == 0) mbar_wait(o_empty(x), (o_cnt & 1u) ^ 1u);  // previous item's epilogue has drained O_x
+          if (j == 0) {  // previous item's epilogue has drained O_x
+            wd_note(my_note, VLA_WD_NOTE(7, x, (o_cnt & 1u) ^ 1u, o_cnt));
+            mbar_wait(o_empty(x), (o_cnt & 1u) ^ 1u);
+          }
           tc_fence_after();
           issue_pv(j);
           if (j + 1 < n_x) {
@@ -573,6 +594,22 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         }
       }
     }
+  } else if (warp_idx == 3) {
+    // ------------------------------------------------------------ watchdog monitor (see common.cuh)
+    wd_monitor(done_bar, note_base, N_WARPS, HD == 64 ? WD_K_FA64 : WD_K_FA72, [&](uint32_t kind, uint32_t idx) {
+      switch (kind) {
+        case 1: return q_empty(idx);
+        case 2: return kv_empty(idx);
+        case 3: return kv_full(idx);
+        case 4: return q_full(idx);
+        case 5: return s_free(idx);
+        case 6: return p_ready(idx);
+        case 7: return o_empty(idx);
+        case 8: return s_full(idx);
+        case 11: return o_full(idx);
+        default: return 0u;  // pv_done / turn notes carry no slot index: the slot follows from the warp number
+      }
+    });
   }
   } else {
     if (L::SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
@@ -612,6 +649,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         int nvalid = p.Skv - k0;
         if (nvalid > BN) nvalid = BN;
         const int nch = (nvalid + 31) >> 5;           // 32-key chunks holding valid keys
+        wd_note(my_note, VLA_WD_NOTE(8, x, s_cnt & 1u, s_cnt));
         mbar_wait(s_full(x), s_cnt & 1u);
         ++s_cnt;
         tc_fence_after();
@@ -643,13 +681,13 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           const uint32_t d_bar = (L::DEALIAS && j > 0) ? pv_done(x) : 0u, d_par = d_cnt & 1u;
           if (L::DEALIAS && j > 0) ++d_cnt;
           if (my_live == 2) {
-            if (masked) fa_softmax_tile<HD, 2, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
-            else fa_softmax_tile<HD, 2, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            if (masked) fa_softmax_tile<HD, 2, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
+            else fa_softmax_tile<HD, 2, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
           } else if (my_live == 1) {
-            if (masked) fa_softmax_tile<HD, 1, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
-            else fa_softmax_tile<HD, 1, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            if (masked) fa_softmax_tile<HD, 1, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
+            else fa_softmax_tile<HD, 1, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
           } else {
-            fa_softmax_tile<HD, 0, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            fa_softmax_tile<HD, 0, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
           }
           if (my_live < my_all) {  // causal chunks above the diagonal: P = 0
             uint32_t z[16];
@@ -665,6 +703,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           // pins the order.
           mbar_arrive(s_free(x));
           if (j > 0) {
+            wd_note(my_note, VLA_WD_NOTE(9, x, d_cnt & 1u, d_cnt));
             mbar_wait(pv_done(x), d_cnt & 1u);
             ++d_cnt;
           }
@@ -683,6 +722,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         named_bar_sync(bar_id, 64);
         l_tot = l + *xo;
       }
+      wd_note(my_note, VLA_WD_NOTE(11, x, o_cnt & 1u, o_cnt));
       mbar_wait_relaxed(o_full(x), o_cnt & 1u);
       ++o_cnt;
       tc_fence_after();
@@ -755,6 +795,10 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   }
 
   if (L::TMA_EPI && warp_idx >= 4 && lane == 0) tma_store_wait<0>();  // output stores have left shared memory
+  if (warp_idx != 3) {  // this warp's role is complete
+    wd_note(my_note, 0xffffffffu);
+    if (lane == 0) mbar_arrive(done_bar);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp_idx == 1) {
@@ -798,16 +842,7 @@ bool make_head_map(CUtensorMap* m, const void* base, int hd, int heads, int rows
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int fa_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int fa_num_sms() { return device_num_sms(); }
 
 // Work list of one (sample, kv head): every (query head of the group, query tile) unit, heaviest first, paired
 // two by two into the slots of one work item.  Returns the number of items, or -1 if the table is too small.
@@ -843,7 +878,8 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
               int Skv, int B, int n_heads, int group, int causal, __nv_bfloat16* out, int ld_out, int q_rows,
               cudaStream_t s, const char** err) {
   using L = FaSmem<HD, BN>;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;  // the shared-memory opt-in is per device
+  bool& attr_set = attr_flag.here();
   if (!attr_set) {
     if (cudaFuncSetAttribute(fa_tcgen05_kernel<HD, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
         cudaSuccess) {
@@ -932,6 +968,12 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
 }
 
 }  // namespace
+
+cudaError_t fa_set_watchdog(WdBuf* dev_ptr, unsigned long long timeout_ms) {
+  cudaError_t e = dev_ptr ? wd_set_buffer_this_tu(dev_ptr) : cudaSuccess;
+  if (e == cudaSuccess && timeout_ms) e = wd_set_limit_this_tu(timeout_ms);
+  return e;
+}
 
 // Returns 1 when the shape is not served by this kernel (caller falls back to the mma.sync kernel), 0 on launch.
 int attention_tc_launch(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, const __nv_bfloat16* v,

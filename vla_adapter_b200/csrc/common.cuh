@@ -133,6 +133,95 @@ VLA_DEVINL void mbar_wait_short(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(20);
 }
 
+// ---------------------------------------------------------------- watchdog
+// A protocol deadlock inside a warp-specialised kernel must not hang the process: every tcgen05 kernel carries one
+// MONITOR warp that does nothing but wait (suspended in mbarrier.try_wait, no issue slots) for the CTA's `done`
+// barrier, on which every working warp arrives when its role loop ends.  If the CTA is still not done after the time
+// limit (10 s; VLA_WATCHDOG_MS / vla_watchdog_set_timeout_ms) the monitor writes, for every warp of the CTA, the note
+// that warp left before its last wait (which barrier, which parity, which step) plus the raw state of that mbarrier to
+// a host-mapped buffer and traps: the hang becomes a CUDA launch failure whose message names the barrier
+// (vla_watchdog_report).  The working warps pay one shared-memory store per wait (wd_note) and no registers - bounding
+// every wait in place was tried first and spilled in the attention kernel's 32-register warps.
+struct WdRecord {
+  uint32_t magic, kernel, block, smid, warp, note, bar_lo, bar_hi;
+};
+constexpr unsigned int WD_MAX_RECORDS = 63;
+struct WdBuf {
+  unsigned int pad[8];
+  WdRecord rec[WD_MAX_RECORDS];
+};
+constexpr uint32_t WD_MAGIC = 0x57444f47u;  // "WDOG"
+enum : uint32_t { WD_K_GEMM1 = 1, WD_K_GEMM2 = 2, WD_K_FA64 = 3, WD_K_FA72 = 4, WD_K_POLICY = 5, WD_K_SELFTEST = 0x7f };
+// note = barrier kind [31:24] | barrier index [23:16] | parity [15] | step [14:0]
+#define VLA_WD_NOTE(kind, idx, parity, step)                                                \
+  ((static_cast<uint32_t>(kind) << 24) | ((static_cast<uint32_t>(idx) & 0xffu) << 16) |   \
+   ((static_cast<uint32_t>(parity) & 1u) << 15) | (static_cast<uint32_t>(step) & 0x7fffu))
+
+// One copy per translation unit (the library is built without -rdc); every TU with a monitored kernel exports a
+// setter built on these and the engine calls them all for its device (watchdog.cu).
+static __device__ WdBuf* g_wd_buf = nullptr;
+static __device__ unsigned int g_wd_slots = 0;  // slot allocation stays in device memory (no PCIe atomics needed)
+static __constant__ uint32_t g_wd_limit_ticks = 9537;  // time limit in units of 2^20 ns (10 s)
+static inline cudaError_t wd_set_buffer_this_tu(WdBuf* host_mapped) {
+  return cudaMemcpyToSymbol(g_wd_buf, &host_mapped, sizeof(host_mapped));
+}
+static inline cudaError_t wd_set_limit_this_tu(unsigned long long timeout_ms) {
+  unsigned long long t = (timeout_ms * 1000000ull) >> 20;
+  const uint32_t ticks = t < 2 ? 2u : (t > 0x7ffffull ? 0x7ffffu : static_cast<uint32_t>(t));
+  return cudaMemcpyToSymbol(g_wd_limit_ticks, &ticks, sizeof(ticks));
+}
+
+VLA_DEVINL unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Working warps: "I am about to wait on this barrier" (all lanes store the same word: one instruction, no branch).
+VLA_DEVINL void wd_note(uint32_t slot_addr, uint32_t note) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot_addr), "r"(note) : "memory");
+}
+// Monitor warp (all 32 lanes): returns when `done_bar` completes; on timeout dumps `n_warps` notes (slots_addr[w]) and
+// the barrier each note names (bar_of(kind, idx) -> shared address or 0), then traps.
+template <class BarOf>
+VLA_DEVINL void wd_monitor(uint32_t done_bar, uint32_t slots_addr, int n_warps, uint32_t kernel, BarOf bar_of) {
+  uint32_t polls = 0, t0 = 0;
+  while (!mbar_try_wait(done_bar, 0)) {
+    __nanosleep(200);
+    if ((++polls & 0x3fffu) != 0) continue;
+    const uint32_t now = static_cast<uint32_t>(global_timer_ns() >> 20) | 1u;
+    if (!t0) {
+      t0 = now;
+      continue;
+    }
+    if (now - t0 <= g_wd_limit_ticks) continue;
+    WdBuf* w = g_wd_buf;
+    if (w) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      for (int wi = static_cast<int>(threadIdx.x & 31u); wi < n_warps; wi += 32) {
+        uint32_t note;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(note) : "r"(slots_addr + 4u * wi));
+        const uint32_t bar = bar_of(note >> 24, (note >> 16) & 0xffu);
+        uint32_t lo = 0, hi = 0;
+        if (bar) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(bar));
+        const unsigned int slot = atomicAdd(&g_wd_slots, 1u);
+        if (slot < WD_MAX_RECORDS) {
+          volatile WdRecord* r = &w->rec[slot];
+          r->kernel = kernel; r->block = blockIdx.x; r->smid = smid; r->warp = static_cast<uint32_t>(wi);
+          r->note = note; r->bar_lo = lo; r->bar_hi = hi;
+          __threadfence_system();
+          r->magic = WD_MAGIC;
+        }
+      }
+      __threadfence_system();
+    }
+    // grace period: monitors of other stuck CTAs get to write their records before the trap takes the context down
+    const unsigned long long t1 = global_timer_ns();
+    while (global_timer_ns() - t1 < 100000000ull) __nanosleep(1000);
+    __trap();
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 VLA_DEVINL void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

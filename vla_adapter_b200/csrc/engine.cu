@@ -10,6 +10,7 @@
 #include "gemm.cuh"
 #include "launch.cuh"
 #include "ops.cuh"
+#include "watchdog.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -33,8 +34,10 @@ constexpr int KP = 592;  // patch vector (588) padded to a multiple of 8
 constexpr int PKV = 1792;
 constexpr float LLM_EPS = 1e-6f, VIT_EPS = 1e-6f, HEAD_EPS = 1e-5f, ROPE_THETA = 1e6f;
 
+// A loaded tensor, kept in the caller's dtype until vla_finalize repacks it (then freed).
 struct Master {
-  float* d = nullptr;
+  void* d = nullptr;
+  int dtype = VLA_F32;
   std::vector<int64_t> shape;
   size_t n = 0;
 };
@@ -63,22 +66,34 @@ struct HeadBlock {
   float gate;
 };
 
-__global__ void cvt_to_f32_kernel(const void* src, int dtype, float* dst, size_t n) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (dtype == VLA_BF16) dst[i] = __bfloat162float(static_cast<const bf16*>(src)[i]);
-  else if (dtype == VLA_F16) dst[i] = __half2float(static_cast<const __half*>(src)[i]);
-  else dst[i] = static_cast<const float*>(src)[i];
-}
+// One repack job of vla_finalize: dst[(r / group) * stride + offset + r % group, c] = cast(src[r, c]).  All jobs of a
+// finalize run in ONE kernel launch (pack_jobs_kernel), split into chunks of PACK_CHUNK elements.
+struct PackJob {
+  const void* src;
+  void* dst;
+  int sdtype;      // vla_dtype of src
+  int dst_f32;     // 1: fp32 destination (biases, norm weights), 0: bf16 (GEMM operands)
+  int rows, cols, dst_ld, group, stride, offset;
+};
+constexpr unsigned int PACK_CHUNK = 16384;
 
-// dst[(r / group) * stride + offset + r % group, c] = bf16(src[r, c])
-__global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int cols, bf16* __restrict__ dst,
-                                 int dst_ld, int group, int stride, int offset) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<size_t>(rows) * cols) return;
-  const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
-  const int dr = (r / group) * stride + offset + r % group;
-  dst[static_cast<size_t>(dr) * dst_ld + c] = __float2bfloat16_rn(src[i]);
+__global__ void __launch_bounds__(256)
+pack_jobs_kernel(const PackJob* __restrict__ jobs, const uint2* __restrict__ chunks) {
+  const uint2 ch = chunks[blockIdx.x];  // (job, first element / PACK_CHUNK)
+  const PackJob j = jobs[ch.x];
+  const size_t total = static_cast<size_t>(j.rows) * j.cols;
+  const size_t lo = static_cast<size_t>(ch.y) * PACK_CHUNK;
+  const size_t hi = lo + PACK_CHUNK < total ? lo + PACK_CHUNK : total;
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float v;
+    if (j.sdtype == VLA_BF16) v = __bfloat162float(static_cast<const bf16*>(j.src)[i]);
+    else if (j.sdtype == VLA_F16) v = __half2float(static_cast<const __half*>(j.src)[i]);
+    else v = static_cast<const float*>(j.src)[i];
+    const int r = static_cast<int>(i / j.cols), c = static_cast<int>(i % j.cols);
+    const size_t o = static_cast<size_t>((r / j.group) * j.stride + j.offset + r % j.group) * j.dst_ld + c;
+    if (j.dst_f32) static_cast<float*>(j.dst)[o] = v;
+    else static_cast<bf16*>(j.dst)[o] = __float2bfloat16_rn(v);
+  }
 }
 
 }  // namespace
@@ -87,7 +102,9 @@ struct vla_engine {
   vla_cfg cfg;
   std::string err;
   bool finalized = false;
-  std::unordered_map<std::string, Master> masters;
+  int device = 0;  // the CUDA device this engine lives on: made current at every entry point
+  std::unordered_map<std::string, Master> masters;  // loaded tensors in their source dtype; freed by vla_finalize
+  std::vector<PackJob> jobs;
   std::vector<void*> allocs;
 
   // derived
@@ -175,6 +192,10 @@ struct vla_engine {
 
   int fail(int code, const std::string& m) {
     err = m;
+    if (code == VLA_ERR_CUDA) {  // a trapped kernel: say which barrier the watchdog caught
+      const std::string wd = vla::watchdog_report();
+      if (!wd.empty()) err += "\n" + wd;
+    }
     return code;
   }
   template <class Tp>
@@ -197,14 +218,51 @@ struct vla_engine {
                                std::to_string(numel));
     return it->second;
   }
-  float* f32(const std::string& name, size_t numel) { return need(name, numel).d; }
-  // pack one [rows, cols] fp32 master into dst (bf16) at a row mapping
+  // ---- repack jobs: queued while vla_finalize walks the architecture, executed by ONE kernel launch (flush_jobs)
+  void enqueue(const Master& m, void* dst, bool dst_f32, int rows, int cols, int dst_ld, int group, int stride,
+               int offset) {
+    PackJob j;
+    j.src = m.d; j.dst = dst; j.sdtype = m.dtype; j.dst_f32 = dst_f32 ? 1 : 0;
+    j.rows = rows; j.cols = cols; j.dst_ld = dst_ld; j.group = group; j.stride = stride; j.offset = offset;
+    jobs.push_back(j);
+  }
+  void flush_jobs() {
+    if (jobs.empty()) return;
+    std::vector<uint2> chunks;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      const size_t total = static_cast<size_t>(jobs[i].rows) * jobs[i].cols;
+      for (size_t c = 0; c * PACK_CHUNK < total; ++c) chunks.push_back(make_uint2(static_cast<unsigned>(i), static_cast<unsigned>(c)));
+    }
+    PackJob* dj = nullptr;
+    uint2* dc = nullptr;
+    cudaError_t ce = cudaMalloc(&dj, jobs.size() * sizeof(PackJob));
+    if (ce == cudaSuccess) ce = cudaMalloc(&dc, chunks.size() * sizeof(uint2));
+    if (ce == cudaSuccess) ce = cudaMemcpy(dj, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(dc, chunks.data(), chunks.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+      pack_jobs_kernel<<<static_cast<unsigned>(chunks.size()), 256>>>(dj, dc);
+      ce = cudaDeviceSynchronize();
+    }
+    if (dj) cudaFree(dj);
+    if (dc) cudaFree(dc);
+    jobs.clear();
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      throw std::runtime_error(std::string("weight repack failed: ") + cudaGetErrorString(ce));
+    }
+  }
+  // fp32 copy of a (small) tensor: biases, norm weights, LayerScale.  A fresh buffer per call - the norm fold adds into
+  // it, and a retried vla_finalize must start from the loaded values again.
+  float* f32(const std::string& name, size_t numel) {
+    const Master& m = need(name, numel);
+    float* dst = dalloc<float>(numel);
+    enqueue(m, dst, true, 1, static_cast<int>(numel), static_cast<int>(numel), 1, 0, 0);
+    return dst;
+  }
+  // pack one [rows, cols] tensor into dst (bf16) at a row mapping
   void pack_into(bf16* dst, int dst_ld, const std::string& name, int rows, int cols, int group, int stride,
                  int offset) {
-    const Master& m = need(name, static_cast<size_t>(rows) * cols);
-    const size_t n = static_cast<size_t>(rows) * cols;
-    pack_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(m.d, rows, cols, dst, dst_ld, group, stride,
-                                                                    offset);
+    enqueue(need(name, static_cast<size_t>(rows) * cols), dst, false, rows, cols, dst_ld, group, stride, offset);
   }
   bf16* pack(const std::string& name, int rows, int cols, int dst_ld = 0) {
     if (!dst_ld) dst_ld = cols;
@@ -231,10 +289,15 @@ struct vla_engine {
     float* dst = dalloc<float>(total);
     int off = 0;
     for (auto& p : parts) {
-      cudaMemcpy(dst + off, need(p.first, p.second).d, sizeof(float) * p.second, cudaMemcpyDeviceToDevice);
+      enqueue(need(p.first, p.second), dst + off, true, 1, p.second, p.second, 1, 0, 0);
       off += p.second;
     }
     return dst;
+  }
+  void free_masters() {
+    for (auto& kv : masters)
+      if (kv.second.d) cudaFree(kv.second.d);
+    masters.clear();
   }
 };
 
@@ -395,7 +458,7 @@ int policy_kv_from_llm(vla_engine* e, int i, const bf16* hs, int B, int L, cudaS
 int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t* ext_ids, const int32_t* aq_index, const float* proprio,
             int B, int L, float* out_norm, float* out_unnorm, bf16* out_last_ha, cudaStream_t s) {
   const int NP = e->NP, T = e->T, A = e->A, P = e->P;
-  vla::pdl_set(B <= 8);  // programmatic dependent launch pays off only when kernels are a few microseconds long
+  vla::PdlScope pdl(B <= 8);  // programmatic dependent launch pays off only when kernels are a few microseconds long
   const int Lext = L + N_AQ + 1;
   const int S = NP + Lext;
   const int M = B * S;
@@ -578,6 +641,11 @@ int vla_create(const vla_cfg* cfg, vla_engine** out) {
   vla_engine* e = new vla_engine();
   e->cfg = *cfg;
   *out = e;
+  if (cudaGetDevice(&e->device) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "cudaGetDevice failed");
+  {
+    const char* werr = nullptr;
+    if (vla::watchdog_install_current_device(&werr)) return e->fail(VLA_ERR_CUDA, werr ? werr : "watchdog install failed");
+  }
   if (const char* ng = getenv("VLA_NO_GRAPH")) e->use_graphs = atoi(ng) ? 0 : 1;
   if (const char* nf = getenv("VLA_NO_NORM_FOLD")) e->fold_norms = atoi(nf) ? 0 : 1;
   const vla_cfg& c = e->cfg;
@@ -614,44 +682,38 @@ int vla_load_tensor(vla_engine* e, const char* name, const void* ptr, int dtype,
   }
   if (numel == 0) return e->fail(VLA_ERR_INVALID, "empty tensor " + n);
   const size_t esz = dtype == VLA_F32 ? 4 : 2;
-  cudaPointerAttributes attr;
-  bool on_device = false;
-  if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess) on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
-  cudaGetLastError();
-  const void* src = ptr;
-  void* staging = nullptr;
-  if (!on_device) {
-    if (cudaMalloc(&staging, numel * esz) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "cudaMalloc failed for staging " + n);
-    if (cudaMemcpy(staging, ptr, numel * esz, cudaMemcpyHostToDevice) != cudaSuccess) {
-      cudaFree(staging);
-      return e->fail(VLA_ERR_CUDA, "H2D copy failed for " + n);
-    }
-    src = staging;
-  }
+  vla::DeviceGuard guard(e->device);
+  // The tensor is kept in ITS dtype (one copy, no kernel): vla_finalize converts and repacks everything in one launch.
   Master m;
   m.n = numel;
+  m.dtype = dtype;
   m.shape.assign(shape, shape + ndim);
   auto old = e->masters.find(n);
-  if (old != e->masters.end() && old->second.n == numel) {
+  if (old != e->masters.end() && old->second.n * (old->second.dtype == VLA_F32 ? 4 : 2) == numel * esz) {
     m.d = old->second.d;
   } else {
-    if (cudaMalloc(&m.d, numel * sizeof(float)) != cudaSuccess) {
-      if (staging) cudaFree(staging);
+    if (old != e->masters.end()) {
+      cudaFree(old->second.d);
+      e->masters.erase(old);
+    }
+    if (cudaMalloc(&m.d, numel * esz) != cudaSuccess) {
+      cudaGetLastError();
       return e->fail(VLA_ERR_CUDA, "cudaMalloc failed for " + n);
     }
-    e->allocs.push_back(m.d);
   }
-  cvt_to_f32_kernel<<<static_cast<unsigned>((numel + 255) / 256), 256>>>(src, dtype, m.d, numel);
-  cudaError_t ce = cudaDeviceSynchronize();
-  if (staging) cudaFree(staging);
-  if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("convert failed: ") + cudaGetErrorString(ce));
+  // cudaMemcpyDefault: `ptr` may be host or device memory.  The stream synchronize makes the copy complete before
+  // the call returns (a device-to-device cudaMemcpy is asynchronous): the caller may free `ptr` right away.
+  cudaError_t ce = cudaMemcpyAsync(m.d, ptr, numel * esz, cudaMemcpyDefault, 0);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(0);
   e->masters[n] = m;
+  if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, "copy failed for " + n + ": " + cudaGetErrorString(ce));
   return VLA_OK;
 }
 
 int vla_set_action_stats(vla_engine* e, const double* hi, const double* lo, const uint8_t* mask) {
   if (!e) return VLA_ERR_INVALID;
   if (!hi || !lo) return e->fail(VLA_ERR_INVALID, "set_action_stats: null statistics");
+  vla::DeviceGuard guard(e->device);
   const int A = e->A;
   std::vector<float> fh(A), fl(A);
   std::vector<uint8_t> fm(A, 1);
@@ -679,7 +741,19 @@ int vla_set_action_stats(vla_engine* e, const double* hi, const double* lo, cons
 int vla_finalize(vla_engine* e) {
   if (!e) return VLA_ERR_INVALID;
   if (e->finalized) return VLA_OK;
+  vla::DeviceGuard guard(e->device);
   const vla_cfg& c = e->cfg;
+  size_t mark = e->allocs.size();
+  // A failed attempt (typically VLA_ERR_MISSING) leaves the engine as it was before the call: the caller may load the
+  // missing tensors and call again.
+  auto rollback = [&]() {
+    for (size_t i = mark; i < e->allocs.size(); ++i) cudaFree(e->allocs[i]);
+    e->allocs.resize(mark);
+    e->jobs.clear();
+    e->dino.blocks.clear(); e->sig.blocks.clear(); e->llm.clear(); e->head.clear();
+    e->hid.clear(); e->head_x.clear(); e->h_kv_blk.clear();
+    e->dev_pix = nullptr;
+  };
   try {
     if (!e->stats_set) {
       std::vector<double> hi(e->A, 1.0), lo(e->A, -1.0);
@@ -691,6 +765,7 @@ int vla_finalize(vla_engine* e) {
       int rc = vla_set_image_norm(e, mean, stdv);
       if (rc) return rc;
     }
+    mark = e->allocs.size();  // the statistics / image table above survive a failed attempt
     build_tower(e, e->dino, "vla.vision_backbone.featurizer.", true, c.dino_depth);
     build_tower(e, e->sig, "vla.vision_backbone.fused_featurizer.", false, c.siglip_depth);
     e->pj_w1 = e->pack("vla.projector.fc1.weight", D_PROJ1, D_VIS);
@@ -724,8 +799,9 @@ int vla_finalize(vla_engine* e) {
     const bool pro = c.variant == VLA_HEAD_PRO;
     const std::string hm = "head.model.";
     const int in_dim = e->A * D_LLM;  // MLPResNet input_dim = input_dim * ACTION_DIM (AH:37)
-    std::vector<std::pair<std::string, int>> pw, pb;
-    std::vector<float> gates(24, 0.f);
+    float* gates_dev = e->dalloc<float>(24);
+    e->wkv_cond_all = e->dalloc<bf16>(static_cast<size_t>(24) * PKV * D_LLM);
+    e->bkv_cond_all = e->dalloc<float>(static_cast<size_t>(24) * PKV);
     for (int i = 0; i < 24; ++i) {
       const std::string b = hm + "mlp_resnet_blocks." + std::to_string(i) + ".";
       HeadBlock w;
@@ -751,28 +827,14 @@ int vla_finalize(vla_engine* e) {
       w.ffn_lnb = e->f32(b + "ffn.0.bias", D_LLM);
       w.wffn = e->pack(b + "ffn.1.weight", D_LLM, D_LLM);
       w.bffn = e->f32(b + "ffn.1.bias", D_LLM);
-      float g = 0.f;
-      cudaMemcpy(&g, e->f32(b + "gating_factor", 1), sizeof(float), cudaMemcpyDeviceToHost);
-      // ratio_g = tanh(g) evaluated in the parameter dtype (bf16), AH:225 / AH:344
-      const float gb = __bfloat162float(__float2bfloat16_rn(g));
-      w.gate = __bfloat162float(__float2bfloat16_rn(std::tanh(gb)));
-      {
-        std::vector<float> gv(PKV, 1.0f);
-        for (int c2 = 0; c2 < D_LLM; ++c2) gv[c2] = w.gate;
-        w.gatevec = e->dalloc<float>(PKV);
-        cudaMemcpy(w.gatevec, gv.data(), PKV * sizeof(float), cudaMemcpyHostToDevice);
-      }
+      e->enqueue(e->need(b + "gating_factor", 1), gates_dev + i, true, 1, 1, 1, 1, 0, 0);
+      // the proprio row is the same for all 24 blocks: its K|V projections become ONE GEMM against the stacked weights
+      e->pack_into(e->wkv_cond_all, D_LLM, b + kc + ".weight", D_LLM, D_LLM, D_LLM, 0, i * PKV);
+      e->pack_into(e->wkv_cond_all, D_LLM, b + vc + ".weight", D_LLM, D_LLM, D_LLM, 0, i * PKV + D_LLM);
+      e->enqueue(e->need(b + kc + ".bias", D_LLM), e->bkv_cond_all + static_cast<size_t>(i) * PKV, true, 1, D_LLM, D_LLM, 1, 0, 0);
+      e->enqueue(e->need(b + vc + ".bias", D_LLM), e->bkv_cond_all + static_cast<size_t>(i) * PKV + D_LLM, true, 1, D_LLM, D_LLM, 1, 0, 0);
+      w.gatevec = e->dalloc<float>(PKV);
       e->head.push_back(w);
-    }
-    {  // the proprio row is the same for all 24 blocks: its K|V projections become ONE GEMM against the stacked weights
-      e->wkv_cond_all = e->dalloc<bf16>(static_cast<size_t>(24) * PKV * D_LLM);
-      e->bkv_cond_all = e->dalloc<float>(static_cast<size_t>(24) * PKV);
-      for (int i = 0; i < 24; ++i) {
-        cudaMemcpy(e->wkv_cond_all + static_cast<size_t>(i) * PKV * D_LLM, e->head[i].wkv_cond,
-                   static_cast<size_t>(PKV) * D_LLM * sizeof(bf16), cudaMemcpyDeviceToDevice);
-        cudaMemcpy(e->bkv_cond_all + static_cast<size_t>(i) * PKV, e->head[i].bkv_cond, PKV * sizeof(float),
-                   cudaMemcpyDeviceToDevice);
-      }
     }
     e->head_ln2w = e->f32(hm + "layer_norm2.weight", D_LLM);
     e->head_ln2b = e->f32(hm + "layer_norm2.bias", D_LLM);
@@ -782,15 +844,37 @@ int vla_finalize(vla_engine* e) {
     e->pp_b1 = e->f32("proprio.fc1.bias", D_LLM);
     e->pp_w2 = e->pack("proprio.fc2.weight", D_LLM, D_LLM);
     e->pp_b2 = e->f32("proprio.fc2.bias", D_LLM);
+    bf16* wfc1 = e->pack(hm + "fc1.weight", D_LLM, in_dim);
+    e->need(hm + "layer_norm1.weight", in_dim);
+    float* ln1_bias = e->f32(hm + "layer_norm1.bias", in_dim);
+    float* fc1_bias = e->f32(hm + "fc1.bias", D_LLM);
+
+    // ---- every conversion / repack queued above runs now, in one kernel launch
+    e->flush_jobs();
+
+    {  // ratio_g = tanh(g) evaluated in the parameter dtype (bf16), AH:225 / AH:344
+      float gates[24];
+      if (cudaMemcpy(gates, gates_dev, sizeof(gates), cudaMemcpyDeviceToHost) != cudaSuccess)
+        throw std::runtime_error("reading the gating factors failed");
+      std::vector<float> gv(PKV, 1.0f);
+      for (int i = 0; i < 24; ++i) {
+        HeadBlock& w = e->head[i];
+        const float gb = __bfloat162float(__float2bfloat16_rn(gates[i]));
+        w.gate = __bfloat162float(__float2bfloat16_rn(std::tanh(gb)));
+        for (int c2 = 0; c2 < D_LLM; ++c2) gv[c2] = w.gate;
+        cudaMemcpy(w.gatevec, gv.data(), PKV * sizeof(float), cudaMemcpyHostToDevice);
+      }
+    }
     // x0 = ReLU(fc1(LayerNorm(0))) = ReLU(fc1.W @ bf16(ln1.bias) + fc1.b): input independent (AH:60-67, 114-116)
     {
-      bf16* wfc1 = e->pack(hm + "fc1.weight", D_LLM, in_dim);
       e->x0 = e->dalloc<bf16>(D_LLM);
       const char* err = nullptr;
-      e->need(hm + "layer_norm1.weight", in_dim);
-      int rc = vla::skinny_linear_launch(e->f32(hm + "layer_norm1.bias", in_dim), 1, in_dim, 1, in_dim, wfc1, in_dim,
-                                         D_LLM, e->f32(hm + "fc1.bias", D_LLM), 2, e->x0, D_LLM, nullptr, 0, &err);
-      if (rc) return e->fail(rc, err ? err : "x0 precompute failed");
+      int rc = vla::skinny_linear_launch(ln1_bias, 1, in_dim, 1, in_dim, wfc1, in_dim, D_LLM, fc1_bias, 2, e->x0, D_LLM,
+                                         nullptr, 0, &err);
+      if (rc) {
+        rollback();
+        return e->fail(rc, err ? err : "x0 precompute failed");
+      }
     }
 
     // ---- norms in front of GEMMs folded into the GEMM weights (once; see fold_norms)
@@ -810,7 +894,10 @@ int vla_finalize(vla_engine* e) {
         if (!rc) rc = vla::fold_norm_launch(w.wgu, 2 * I_LLM, D_LLM, D_LLM, w.ln2, nullptr, nullptr, nullptr, nullptr, &err);
       }
       if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = VLA_ERR_CUDA;
-      if (rc) return e->fail(rc, err ? err : "norm fold failed");
+      if (rc) {
+        rollback();
+        return e->fail(rc, err ? err : "norm fold failed");
+      }
     }
 
     // ---- workspace
@@ -849,11 +936,11 @@ int vla_finalize(vla_engine* e) {
     if (e->small_B) {
       for (int i = 0; i < 24; ++i)
         e->h_kv_blk.push_back(e->dalloc<bf16>(static_cast<size_t>(e->small_B) * (e->T + N_AQ + 1 + e->NP) * PKV));
-      if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess)
-        return e->fail(VLA_ERR_CUDA, "side stream creation failed");
-      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
-      for (int i = 0; i < 24; ++i) {
+      if (!e->side && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess)
+        throw std::runtime_error("side stream creation failed");
+      if (!e->ev_fork) cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+      if (!e->ev_join) cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
+      for (int i = static_cast<int>(e->ev_layer.size()); i < 24; ++i) {
         cudaEvent_t a = nullptr, b = nullptr;
         cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
@@ -875,18 +962,20 @@ int vla_finalize(vla_engine* e) {
     int rc = vla::rope_table_launch(e->rope_cos, e->rope_sin, S, 32, ROPE_THETA, 0, &err);
     e->rope_cs = e->dalloc<uint32_t>(static_cast<size_t>(S) * 32);
     if (!rc) rc = vla::rope_pack_launch(e->rope_cos, e->rope_sin, S, e->rope_cs, 0, &err);
-    if (rc) return e->fail(rc, err ? err : "rope table failed");
+    if (rc) throw std::runtime_error(err ? err : "rope table failed");
     const int max_pos = e->NP > 65 ? e->NP : 65;
     e->prope_cos = e->dalloc<float>(static_cast<size_t>(max_pos) * 112);
     e->prope_sin = e->dalloc<float>(static_cast<size_t>(max_pos) * 112);
     rc = vla::policy_rope_table_launch(e->prope_cos, e->prope_sin, max_pos, 0, &err);
-    if (rc) return e->fail(rc, err ? err : "policy rope table failed");
+    if (rc) throw std::runtime_error(err ? err : "policy rope table failed");
     cudaError_t ce = cudaDeviceSynchronize();
-    if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("finalize: ") + cudaGetErrorString(ce));
+    if (ce != cudaSuccess) throw std::runtime_error(std::string("finalize: ") + cudaGetErrorString(ce));
   } catch (const std::exception& ex) {
     const std::string m = ex.what();
+    rollback();
     return e->fail(m.rfind("missing tensor", 0) == 0 ? VLA_ERR_MISSING : (m.rfind("tensor ", 0) == 0 ? VLA_ERR_INVALID : VLA_ERR_CUDA), m);
   }
+  e->free_masters();  // every weight now lives in its repacked form only
   e->finalized = true;
   return VLA_OK;
 }
@@ -900,6 +989,7 @@ static int predict_impl(vla_engine* e, const void* pixel_values, int is_u8, cons
     return e->fail(VLA_ERR_INVALID, "vla_predict: null input/output pointer");
   if (B < 1 || B > e->maxB) return e->fail(VLA_ERR_INVALID, "vla_predict: batch outside [1, max_batch]");
   if (L < 1 || L > e->maxL) return e->fail(VLA_ERR_INVALID, "vla_predict: prompt length outside [1, max_prompt_len]");
+  vla::DeviceGuard guard(e->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bf16* pix = is_u8 ? nullptr : static_cast<const bf16*>(pixel_values);
   const uint8_t* pix8 = is_u8 ? static_cast<const uint8_t*>(pixel_values) : nullptr;
@@ -977,6 +1067,7 @@ int vla_predict_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids,
 int vla_set_image_norm(vla_engine* e, const float* mean, const float* stdv) {
   if (!e) return VLA_ERR_INVALID;
   if (!mean || !stdv) return e->fail(VLA_ERR_INVALID, "set_image_norm: null statistics");
+  vla::DeviceGuard guard(e->device);
   // ToTensor (u8 / 255), Normalize ((x - mean) / std) in fp32 like torchvision, then the bf16 cast of the caller
   std::vector<bf16> lut(2 * 3 * 256);
   for (int t = 0; t < 2; ++t)
@@ -1008,6 +1099,7 @@ static int predict_host_impl(vla_engine* e, const void* pixel_values, int is_u8,
     return e->fail(VLA_ERR_INVALID, "vla_predict_host: null input/output pointer");
   if (B < 1 || B > e->maxB) return e->fail(VLA_ERR_INVALID, "vla_predict_host: batch outside [1, max_batch]");
   if (L < 1 || L > e->maxL) return e->fail(VLA_ERR_INVALID, "vla_predict_host: prompt length outside [1, max_prompt_len]");
+  vla::DeviceGuard guard(e->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t pix_b = static_cast<size_t>(e->maxB) * 6 * e->cfg.n_images * 224 * 224 * 2;
   const size_t ids_b = static_cast<size_t>(e->maxB) * (e->maxL + N_AQ + 1) * 8;
@@ -1073,6 +1165,7 @@ int vla_predict_host_u8(vla_engine* e, const uint8_t* images, const int64_t* ext
 int vla_get_tap(vla_engine* e, const char* name, void* dst, size_t capacity, size_t* bytes) {
   if (!e) return VLA_ERR_INVALID;
   if (!name || !e->lastB) return e->fail(VLA_ERR_INVALID, "get_tap: no forward has run yet");
+  vla::DeviceGuard guard(e->device);
   const std::string n(name);
   const int B = e->lastB, L = e->lastL, NP = e->NP;
   const int S = NP + L + N_AQ + 1;
@@ -1108,6 +1201,7 @@ int vla_get_tap(vla_engine* e, const char* name, void* dst, size_t capacity, siz
 
 int vla_segment_timing(vla_engine* e, int enable) {
   if (!e) return VLA_ERR_INVALID;
+  vla::DeviceGuard guard(e->device);
   if (enable && !e->seg_ev[0])
     for (int i = 0; i < 4; ++i)
       if (cudaEventCreate(&e->seg_ev[i]) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "segment event creation failed");
@@ -1118,10 +1212,30 @@ int vla_segment_timing(vla_engine* e, int enable) {
 int vla_segment_times(vla_engine* e, float* ms3) {
   if (!e) return VLA_ERR_INVALID;
   if (!ms3 || !e->seg_ev[0]) return e->fail(VLA_ERR_INVALID, "segment_times: timing was never enabled");
+  vla::DeviceGuard guard(e->device);
   if (cudaEventSynchronize(e->seg_ev[3]) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "segment_times: no timed forward yet");
   for (int i = 0; i < 3; ++i)
     if (cudaEventElapsedTime(&ms3[i], e->seg_ev[i], e->seg_ev[i + 1]) != cudaSuccess)
       return e->fail(VLA_ERR_CUDA, "segment_times: events not recorded");
+  return VLA_OK;
+}
+
+// The device-pointer calls (vla_predict, vla_predict_u8) are asynchronous and cannot report what the kernels find:
+// this call waits for `stream`, then reports (and clears) the device-side error flag - an out-of-range token id or
+// ActionQuery index (the offending row of the LLM input was zero-filled) - and any CUDA error of the forward.
+int vla_check_errors(vla_engine* e, void* stream) {
+  if (!e) return VLA_ERR_INVALID;
+  if (!e->finalized) return e->fail(VLA_ERR_NOT_FINALIZED, "vla_check_errors before vla_finalize");
+  vla::DeviceGuard guard(e->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int flag = 0;
+  cudaError_t ce = cudaMemcpyAsync(&flag, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("forward failed: ") + cudaGetErrorString(ce));
+  if (flag) {
+    cudaMemsetAsync(e->err_flag, 0, sizeof(int), s);
+    return e->fail(VLA_ERR_INVALID, flag == 1 ? "token id outside [0, vocab_size)" : "ActionQuery index outside [0, 64)");
+  }
   return VLA_OK;
 }
 
@@ -1131,6 +1245,7 @@ const char* vla_last_error(const vla_engine* e) { return e ? e->err.c_str() : "n
 
 void vla_destroy(vla_engine* e) {
   if (!e) return;
+  vla::DeviceGuard guard(e->device);
   cudaDeviceSynchronize();
   for (auto& g : e->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -1145,6 +1260,7 @@ void vla_destroy(vla_engine* e) {
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->side) cudaStreamDestroy(e->side);
   for (void* p : e->allocs) cudaFree(p);
+  e->free_masters();
   delete e;
 }
 

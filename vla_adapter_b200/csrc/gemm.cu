@@ -7,16 +7,19 @@
 // (modeling_prismatic.py:261-273), Qwen2's q/k/v/o/gate/up/down, and the Bridge-Attention policy's
 // q/k/v/o/ffn projections (action_heads.py:247-254, 355-367).
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 352 threads):
 //   warp 0   : TMA producer  - cp.async.bulk.tensor (3-D maps, 128B swizzle) into a STAGES-deep ring
 //   warp 1   : MMA issuer    - one thread issues tcgen05.mma (M=128, N=BN, K=16) from smem descriptors
-//   warps 2-5: epilogue      - tcgen05.ld the fp32 accumulator out of TMEM, bias/act/scale/residual,
-//                              cast to bf16, vectorised global stores
+//   warps 2-9: epilogue      - tcgen05.ld the fp32 accumulator out of TMEM, bias/act/scale/residual,
+//                              cast to bf16, swizzled smem staging, TMA store / reduce-add
+//   warp 10  : watchdog monitor (common.cuh): parked on the CTA's `done` barrier; dumps every warp's last wait and
+//              traps if the CTA does not finish within the time limit
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
 #include "common.cuh"
 #include "launch.cuh"
 #include "gemm.cuh"
+#include "watchdog.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -30,7 +33,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int GEMM_THREADS = 352;          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue, warp 10 watchdog monitor
+constexpr int GEMM_WORK_WARPS = 10;
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB per stage
 constexpr uint32_t RING_BYTES = 192 * 1024;
@@ -117,6 +121,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  const uint32_t done_bar = bar_base + 8u * (2 * MAX_STAGES + 5);        // watchdog: every working warp arrives at its end
+  const uint32_t note_base = bar_base + 8u * (2 * MAX_STAGES + 6);       // watchdog: one "last wait" word per warp
 
   // Warp index broadcast with shfl so the compiler knows the role branches are warp-uniform: the MMA warp's
   // descriptor arithmetic then stays on the uniform datapath and tcgen05.mma issues at the hardware rate
@@ -136,6 +142,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EPI_WARPS * CG);  // the leader's barrier collects the epilogue warps of both CTAs
     }
+    mbar_init(done_bar, GEMM_WORK_WARPS);
     mbar_fence_init();
     fence_proxy_async();
   }
@@ -160,6 +167,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
   const int num_kb = (p.K + BK - 1) / BK;
   const int total_tiles = p.tiles_m * p.tiles_n;  // tiles of (BM * CG) rows x bn columns
   const int tile0 = static_cast<int>(blockIdx.x) / CG, tile_step = static_cast<int>(gridDim.x) / CG;
+  const uint32_t my_note = note_base + 4u * static_cast<uint32_t>(warp_idx);
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp waits, one lane issues)
@@ -173,6 +181,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       const int r0 = p.pack ? 0 : (m_idx - b * p.mt_per_batch) * (BM * CG) + static_cast<int>(crank) * BM;
       const int n0 = n_idx * p.bn + static_cast<int>(crank) * (p.bn / CG);
       for (int kb = 0; kb < num_kb; ++kb) {
+        wd_note(my_note, VLA_WD_NOTE(1, stage, phase ^ 1u, kb));
         mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);  // the ring is deep: the producer mostly waits, politely
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -203,10 +212,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     uint32_t acc_phase = 0;
     if (crank == 0)  // only the leader of a pair issues MMAs
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      wd_note(my_note, VLA_WD_NOTE(3, acc, acc_phase ^ 1u, tile));
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
       for (int kb = 0; kb < num_kb; ++kb) {
+        wd_note(my_note, VLA_WD_NOTE(2, stage, phase, kb));
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
@@ -237,6 +248,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+  } else if (warp_idx == GEMM_WORK_WARPS) {
+    // ------------------------------------------------------------ watchdog monitor (see common.cuh)
+    wd_monitor(done_bar, note_base, GEMM_WORK_WARPS, CG == 2 ? WD_K_GEMM2 : WD_K_GEMM1, [&](uint32_t kind, uint32_t idx) {
+      return kind == 1 ? empty_bar(idx) : kind == 2 ? full_bar(idx) : kind == 3 ? tempty_bar(idx) : kind == 4 ? tfull_bar(idx) : 0u;
+    });
   } else {
     // ------------------------------------------------------------ epilogue: 8 warps, each 32 rows x bn/2 columns
     const int e = warp_idx - 2;
@@ -264,6 +280,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       float2 rst = make_float2(1.f, 0.f);  // this thread's row: (rstd, -mean * rstd)
       if (p.row_stats && r0 + lane < p.rows) rst = __ldg(p.row_stats + r0 + lane);
 
+      wd_note(my_note, VLA_WD_NOTE(4, acc, acc_phase, tile));
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -431,6 +448,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     }
     if (lane == 0) tma_store_wait_read<0>();  // staging smem must outlive the last bulk reads
   }
+  if (warp_idx < GEMM_WORK_WARPS) {  // this warp's role is complete
+    wd_note(my_note, 0xffffffffu);
+    if (lane == 0) mbar_arrive(done_bar);
+  }
 
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // neither CTA may leave while the pair's MMAs / remote arrivals can touch it
@@ -511,20 +532,17 @@ bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 std::mutex g_prof_mu;
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return device_num_sms(); }
 
 }  // namespace
 
 long long gemm_launch_count() { return g_launches.load(); }
+
+cudaError_t gemm_set_watchdog(WdBuf* dev_ptr, unsigned long long timeout_ms) {
+  cudaError_t e = dev_ptr ? wd_set_buffer_this_tu(dev_ptr) : cudaSuccess;
+  if (e == cudaSuccess && timeout_ms) e = wd_set_limit_this_tu(timeout_ms);
+  return e;
+}
 
 int copy_view_launch(const __nv_bfloat16* src, long long s_bs, int lds, __nv_bfloat16* dst, long long d_bs, int ldd,
                      int rows, int batches, int cols, cudaStream_t stream, const char** err) {
@@ -605,7 +623,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     if (err) *err = "gemm: a folded norm needs row_stats, one row view, and no mean term with SwiGLU";
     return -1;
   }
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;  // the shared-memory opt-in is per device
+  bool& attr_set = attr_flag.here();
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              SMEM_BYTES) != cudaSuccess ||

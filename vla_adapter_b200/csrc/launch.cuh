@@ -10,21 +10,67 @@
 namespace vla {
 
 // Measured on B200: PDL shortens the bs=1 forward by ~5 % (prologues overlap the 6-8 us kernels) but costs ~4 % at
-// bs=64 (early-resident CTAs of the next kernel compete with the draining one), so the engine switches it per call:
-// on for small batches, off for large ones.  VLA_PDL=0/1 forces it.
+// bs=64 (early-resident CTAs of the next kernel compete with the draining one), so the engine chooses per forward:
+// on for small batches, off for large ones.  The choice is the calling thread's (PdlScope in forward()), not a
+// process global: engines on different devices / threads do not see each other's setting.  VLA_PDL=0/1 forces it.
 inline int& pdl_flag() {
-  static int v = 1;
+  static thread_local int v = 0;
   return v;
 }
-inline void pdl_set(bool on) {
-  static int forced = -1;
-  if (forced < 0) {
+inline int pdl_forced() {
+  static const int forced = [] {
     const char* e = getenv("VLA_PDL");
-    forced = e ? (atoi(e) != 0 ? 1 : 0) : 2;
-  }
-  pdl_flag() = forced == 2 ? (on ? 1 : 0) : forced;
+    return e ? (atoi(e) != 0 ? 1 : 0) : 2;
+  }();
+  return forced;
 }
+struct PdlScope {
+  int saved;
+  explicit PdlScope(bool on) : saved(pdl_flag()) {
+    const int f = pdl_forced();
+    pdl_flag() = f == 2 ? (on ? 1 : 0) : f;
+  }
+  ~PdlScope() { pdl_flag() = saved; }
+  PdlScope(const PdlScope&) = delete;
+  PdlScope& operator=(const PdlScope&) = delete;
+};
 inline bool pdl_enabled() { return pdl_flag() != 0; }
+
+// Per-device one-time state (cudaFuncSetAttribute is per device, and so is the SM count): indexed by the CURRENT
+// device of the calling thread.  The engine makes its device current at every C-ABI entry point.
+constexpr int VLA_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= VLA_MAX_DEVICES) dev = 0;
+  return dev;
+}
+struct PerDeviceFlag {
+  bool done[VLA_MAX_DEVICES] = {};
+  bool& here() { return done[current_device()]; }
+};
+inline int device_num_sms() {
+  static int n[VLA_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
+  }
+  return n[dev];
+}
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // cluster_x > 1 launches thread-block clusters of that many CTAs along x (CTA pairs for cta_group::2 kernels).
 template <typename... KArgs, typename... Args>

@@ -371,24 +371,26 @@ assemble_kernel(__nv_bfloat16* __restrict__ x, int B, int S, int NP, int Lext, i
   const int b = blockIdx.x / Lext;
   const int s = (j == 0) ? 0 : NP + j;
   const int aq = aq_index[static_cast<long long>(b) * Lext + j];
-  const __nv_bfloat16* src;
+  // An out-of-range id / index raises the device flag (vla_check_errors, vla_predict_host) and the row is ZERO-filled:
+  // the call's result is then deterministic garbage for that sample, never a stale row of an earlier call.
+  const __nv_bfloat16* src = nullptr;
   if (aq >= 0) {
     if (aq >= n_aq) {
       if (threadIdx.x == 0) atomicExch(err_flag, 2);
-      return;
+    } else {
+      src = aq_table + static_cast<long long>(aq) * dim;
     }
-    src = aq_table + static_cast<long long>(aq) * dim;
   } else {
     const int64_t id = ext_ids[static_cast<long long>(b) * Lext + j];
     if (id < 0 || id >= vocab) {
       if (threadIdx.x == 0) atomicExch(err_flag, 1);
-      return;
+    } else {
+      src = embed + id * dim;
     }
-    src = embed + id * dim;
   }
   __nv_bfloat16* dst = x + (static_cast<long long>(b) * S + s) * dim;
   for (int v = threadIdx.x; v < (dim >> 3); v += blockDim.x)
-    reinterpret_cast<uint4*>(dst)[v] = __ldg(reinterpret_cast<const uint4*>(src) + v);
+    reinterpret_cast<uint4*>(dst)[v] = src ? __ldg(reinterpret_cast<const uint4*>(src) + v) : make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ------------------------------------------------------------------ skinny linear
