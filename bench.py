@@ -165,6 +165,41 @@ def workload_name(B: int, L: int, variant: str) -> str:
             f"L={L} prompt, 64 ActionQuery, proprio, {T_CHUNK}x{A_DIM} chunk, {variant} head")
 
 
+def gpu_eager_baseline(dev, pro: bool, B: int, L: int):
+    """The path's algorithm as plain PyTorch eager ops on the GPU (the oracle's torch code moved to `dev`, bf16 like the
+    reference requires): what a user of the reference gets from one B200 today, minus the reference's discarded work
+    (lm_head, last ViT blocks).  bs=1 calls (the only mode the reference supports, MP:855) and ONE batched call."""
+    from oracle import vla_oracle as O
+    ocfg = O.OracleConfig(n_images=N_IMAGES, pro=pro, chunk_len=T_CHUNK, action_dim=A_DIM, proprio_dim=P_DIM,
+                          vocab_size=4096)
+    OW = {k: v.to(dev, torch.bfloat16) for k, v in O.make_weights(ocfg, seed=0).items()}
+    opix, oids, oprop = (t.to(dev) for t in O.make_inputs(ocfg, B, L, seed=0))
+
+    def run(n):
+        with torch.no_grad(), torch.device(dev):
+            return O.predict_action_batch(OW, ocfg, opix[:n], oids[:n], oprop[:n], torch.bfloat16)["normalized"]
+
+    def timed(n, reps):
+        best = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run(n)
+            torch.cuda.synchronize()
+            best.append(time.perf_counter() - t0)
+        return statistics.median(best)
+
+    run(1)
+    run(1)
+    t1 = timed(1, 7)
+    run(B)
+    tb = timed(B, 3)
+    return {"bs1_ms": t1 * 1e3, "bs1_chunks_per_s": 1.0 / t1, "batched_ms": tb * 1e3, "batched_chunks_per_s": B / tb,
+            "batch": B, "unit": UNIT,
+            "what": "oracle port (torch eager ops: cuBLAS matmuls, softmax(QK^T)V attention) on the same GPU, bf16, "
+                    "median wall clock; bs=1 is the reference's only mode, the batched call is what eager PyTorch could do"}
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm (oracle port, bf16 like the reference requires) on all host
     cores.  Each step is a bounded sample of the step's batch: ONE observation (1/B of the batch)."""
@@ -175,15 +210,27 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = O.OracleConfig(n_images=N_IMAGES, pro=args.variant == "pro", chunk_len=T_CHUNK, action_dim=A_DIM,
-                         proprio_dim=P_DIM)
+                         proprio_dim=P_DIM, vocab_size=4096)  # the embedding table is only gathered from
     W = O.make_weights(cfg, seed=0)
     pix, ids, prop = O.make_inputs(cfg, 1, PROMPT_LEN, seed=0)
+    # The UNMODIFIED reference (its own predict_action through oracle/ref_shim.py) where its sources are mounted -
+    # the build container - and the LIBERO constants apply; on the GPU box /root/reference does not exist and the
+    # oracle port of the same algorithm is timed instead.
+    kind, call = "port", (lambda: O.predict_action_batch(W, cfg, pix, ids, prop, torch.bfloat16))
+    try:
+        from oracle import ref_shim as R
+        if R.available() and (T_CHUNK, A_DIM, P_DIM) == (8, 7, 8):
+            stats = {"synthetic": {"action": {"q01": [-1.0] * A_DIM, "q99": [1.0] * A_DIM}}}
+            ns, vla, head, pp = R.build_reference(cfg, W, torch.bfloat16, norm_stats=stats)
+            kind, call = "reference", (lambda: R.reference_predict_action(ns, vla, head, pp, pix, ids, prop, "synthetic"))
+    except Exception as ex:  # the shim needs the reference's sources and transformers; fall back to the port
+        print(f"[bench] reference shim unavailable ({type(ex).__name__}: {ex}); timing the oracle port", file=sys.stderr)
     budget_s = args.ref_budget
     times = []
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        O.predict_action_batch(W, cfg, pix, ids, prop, torch.bfloat16)
+        call()
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
@@ -192,8 +239,9 @@ def run_reference(args):
             break
     ms = statistics.mean(times) * 1e3
     val = 1000.0 / ms
-    sample = (f"1 observation per step (1/{args.batch} of the bs={args.batch} batch), bf16 torch-CPU oracle, "
-              f"{len(times)} timed steps of the requested {args.steps}")
+    sample = (f"1 observation per step (1/{args.batch} of the bs={args.batch} batch), bf16 on the host CPU, "
+              + ("the unmodified reference's predict_action" if kind == "reference" else "torch-CPU oracle port")
+              + f", {len(times)} timed steps of the requested {args.steps}")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -201,7 +249,7 @@ def run_reference(args):
         # the same workload as our arm; this arm times a bounded sample of it (one observation per step, see `sample`)
         "config": {"workload": workload_name(args.batch, PROMPT_LEN, args.variant), "global_batch": args.gpus * args.batch,
                    "per_gpu_batch": args.batch, "sampled_observations_per_step": 1},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -219,6 +267,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=200.0, help="wall-clock bound [s] of the reference arm")
     ap.add_argument("--latency-iters", type=int, default=200, help="bs=1 latency samples (after 20 warm-up calls)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch samples per GPU; strong: --batch is the GLOBAL batch, split over the ranks "
+                         "(SURVEY 8d config 4 asks for both)")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--chunk", default="8x7x8", help="chunk_len x action_dim x proprio_dim: 8x7x8 = LIBERO / CALVIN "
                     "(constants.py:28-40), 25x14x14 = the reference's larger-chunk preset (ALOHA, constants.py:42-47)")
     args = ap.parse_args()
@@ -260,6 +312,10 @@ def main():
     from vla_adapter_b200 import sharding
 
     B, L, K, Wu = args.batch, PROMPT_LEN, args.steps, args.warmup
+    if args.scaling == "strong":
+        if B % world:
+            raise SystemExit(f"--scaling strong: the global batch {B} must divide over {world} ranks")
+        B //= world
     pro = args.variant == "pro"
     eng = VLAEngine(n_images=N_IMAGES, chunk_len=T_CHUNK, action_dim=A_DIM, proprio_dim=P_DIM, pro=pro, max_batch=B,
                     max_prompt_len=L, device=local,
@@ -397,20 +453,34 @@ def main():
 
     # ---------------- bs=1 latency through the host path (p50 / p90), BASELINE.json's second metric
     stage("bs=1 latency")
-    lat = []
     one = [t[:1].contiguous().pin_memory() for t in (pix_h, ext_h, aq_h, prop_h)]
     o1, o2 = on_h[:1].clone().pin_memory(), ou_h[:1].clone().pin_memory()
-    for i in range(args.latency_iters + 20 if args.latency_iters > 0 else 0):
-        t0 = time.perf_counter()
-        eng.predict_host(one[0], one[1], one[2], one[3], o1, o2)
-        if i >= 20:
-            lat.append((time.perf_counter() - t0) * 1e3)
-    lat.sort()
-    latency = None
-    if lat:
-        latency = {"p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "iters": len(lat),
-                   "warmup": 20,
-                   "how": "wall clock around vla_predict_host(B=1) incl. H2D/D2H and stream sync"}
+
+    def bs1_latency(engine, head):
+        lat = []
+        for i in range(args.latency_iters + 20 if args.latency_iters > 0 else 0):
+            t0 = time.perf_counter()
+            engine.predict_host(one[0], one[1], one[2], one[3], o1, o2)
+            if i >= 20:
+                lat.append((time.perf_counter() - t0) * 1e3)
+        lat.sort()
+        if not lat:
+            return None
+        return {"head": head, "p50_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "iters": len(lat),
+                "warmup": 20, "how": "wall clock around vla_predict_host(B=1) incl. H2D/D2H and stream sync"}
+
+    latency = bs1_latency(eng, args.variant)
+    # BASELINE.json configs[1] asks for the bs=1 latency of BOTH heads: a second, bs=1-sized engine with the other head
+    latency_other = None
+    if world == 1 and latency is not None:
+        other = "base" if pro else "pro"
+        stage(f"bs=1 latency, {other} head")
+        eng1 = VLAEngine(n_images=N_IMAGES, chunk_len=T_CHUNK, action_dim=A_DIM, proprio_dim=P_DIM, pro=not pro,
+                         max_batch=1, max_prompt_len=L, device=local)
+        load_random_weights(eng1, seed=0, n_images=N_IMAGES, action_dim=A_DIM, proprio_dim=P_DIM, pro=not pro)
+        eng1.finalize()
+        latency_other = bs1_latency(eng1, other)
+        eng1.close()
 
     # ---------------- CPU baseline (rank 0, N=1 only): the oracle on this box's cores, bounded sample
     stage("CPU baseline (oracle)")
@@ -435,10 +505,19 @@ def main():
                "sample": "1 observation per call (1/%d of the batch), bf16 torch-CPU oracle, median of %d calls after "
                          "1 warm-up, embedding table cut to 4096 rows (gather only)" % (B, len(dts))}
 
+    # ---------------- like-for-like GPU baseline: the same algorithm in PyTorch eager on this GPU
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager_baseline:
+        stage("GPU eager baseline (oracle port in PyTorch eager, bf16, on this GPU)")
+        try:
+            gpu_eager = gpu_eager_baseline(dev, pro, B, L)
+        except Exception as ex:  # a baseline must never take the measurement down with it
+            gpu_eager = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wu,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(B, L, args.variant),
                        "global_batch": world * B, "per_gpu_batch": B, "params": n_params,
@@ -452,6 +531,7 @@ def main():
                                  "note": "vla_predict_host_u8: uint8 HWC frames, normalisation on the device"},
             "gpu_launches": int(launches),
             "roofline": roofline, "step_roofline": step_roofline, "segments": segments, "latency_bs1": latency,
+            "latency_bs1_other_head": latency_other, "gpu_eager_baseline": gpu_eager,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

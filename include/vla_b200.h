@@ -93,21 +93,26 @@ int vla_finalize(vla_engine* e);
  *   ext_ids      : device, int64, (B, L+65) = prompt ids, 64 placeholder ids, STOP   (MP:748-758)
  *   aq_index     : device, int32, (B, L+65): ActionQuery row to splice at that column or -1
  *                  (the all_actions_mask / masked_indices of MP:442-452, as indices)
+ *   prompt_len   : device, int32, (B) prompt lengths L_b in [1, L], or NULL when every prompt has L tokens.  With
+ *                  lengths, row b of ext_ids / aq_index is RIGHT-padded: [ids(L_b) | 64 placeholders | STOP | pad], pad
+ *                  columns holding any valid id and aq_index -1.  The reference is bs=1 and never pads (MP:855); chat
+ *                  prompts span 40-56 tokens (openvla_utils.py:783), so a served batch mixes lengths.  Causal attention
+ *                  keeps every real row identical to the un-padded run of that sample.
  *   proprio      : device, fp32, (B, proprio_dim), already normalised (openvla_utils.py:671-701)
  *   out_norm     : device, fp32, (B, chunk_len, action_dim) normalised actions      (MP:871-872)
  *   out_unnorm   : device, fp32, (B, chunk_len, action_dim) un-normalised actions   (MP:799-803)
  *   out_last_ha  : device, bf16, (B, 64, 896) last-layer ActionQuery states or NULL (MP:855, 972)
  */
 int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
-                const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm,
-                float* out_unnorm, void* out_last_ha, void* stream);
+                const int32_t* aq_index, const int32_t* prompt_len, const float* proprio, int B, int L,
+                float* out_norm, float* out_unnorm, void* out_last_ha, void* stream);
 
 /* Same call with HOST buffers (pinned or pageable): the engine stages inputs through its own
  * pinned buffers, runs vla_predict and copies the results back; synchronises the stream.
  * This is the end-to-end path bench.py reports as `e2e`. */
 int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext_ids,
-                     const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm,
-                     float* out_unnorm, void* out_last_ha, void* stream);
+                     const int32_t* aq_index, const int32_t* prompt_len, const float* proprio, int B, int L,
+                     float* out_norm, float* out_unnorm, void* out_last_ha, void* stream);
 
 /* Device-side image front-end: the same forward from uint8 frames.  `images` is
  * (B, n_images, 224, 224, 3) uint8, HWC, already resized / centre-cropped like PrismaticImageProcessor.apply_transform
@@ -116,11 +121,11 @@ int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext
  * built with the processor's fp32 arithmetic, so results are bit-identical to feeding the CPU-normalised pixel_values
  * to vla_predict.  vla_predict_u8 takes device pointers, vla_predict_host_u8 host pointers (H2D / D2H inside). */
 int vla_predict_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids, const int32_t* aq_index,
-                   const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
-                   void* stream);
+                   const int32_t* prompt_len, const float* proprio, int B, int L, float* out_norm, float* out_unnorm,
+                   void* out_last_ha, void* stream);
 int vla_predict_host_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids, const int32_t* aq_index,
-                        const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
-                        void* stream);
+                        const int32_t* prompt_len, const float* proprio, int B, int L, float* out_norm,
+                        float* out_unnorm, void* out_last_ha, void* stream);
 /* Normalisation statistics of the two backbones, mean[2][3] / std[2][3] (backbone 0 = DINOv2, 1 = SigLIP; the
  * defaults are those of pretrained_models/configs/preprocessor_config.json).  May be called before or after
  * vla_finalize. */

@@ -39,16 +39,22 @@ STATS = {"synthetic": {"action": {"q01": [-0.9, -0.8, -1.0, -0.5, -0.25, -0.1, 0
                                   "mask": [True, True, True, True, True, True, False]}}}
 
 CASES = {
-    # name: (pro, n_images, B, L, seed)
-    "libero_base": (False, 2, 2, 20, 0),
-    "libero_pro": (True, 2, 1, 33, 1),
-    "single_image": (False, 1, 1, 31, 2),
+    # name: (pro, n_images, B, L, seed, dino_depth, siglip_depth)
+    "libero_base": (False, 2, 2, 20, 0, 3, 3),
+    "libero_pro": (True, 2, 1, 33, 1, 3, 3),
+    # NOT a reference-pinned deployment case: with one image the reference's own glue would still build the head with
+    # num_task_tokens = 512 (openvla_utils.py:505, AH:28) and mis-split h_t / h_a; the shim builds it with 256, which
+    # is what the engine and the oracle implement.  Kept as a pin of the n = 1 arithmetic only.
+    "single_image": (False, 1, 1, 31, 2, 3, 3),
+    # the FULL-DEPTH architecture of BASELINE.json (DINOv2 24 / SigLIP 27 blocks, 24 LLM layers, 24 policy blocks,
+    # L = 48), bs = 1, through the unmodified reference; only the vocabulary is cut (gather only)
+    "libero_full_pro": (True, 2, 1, 48, 3, 24, 27),
 }
 
 
 def case_config(name):
-    pro, n_images, B, L, seed = CASES[name]
-    cfg = O.OracleConfig(n_images=n_images, dino_depth=3, siglip_depth=3, vocab_size=2048, pro=pro)
+    pro, n_images, B, L, seed, dd, sd = CASES[name]
+    cfg = O.OracleConfig(n_images=n_images, dino_depth=dd, siglip_depth=sd, vocab_size=2048, pro=pro)
     return cfg, B, L, seed
 
 

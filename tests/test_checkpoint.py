@@ -78,8 +78,19 @@ def test_loader_errors(tmp_path):
     with pytest.raises(AssertionError):
         CK.load_checkpoint(str(tmp_path), _FakeEngine)
     os.remove(os.path.join(str(tmp_path), "action_head--2_checkpoint.pt"))
-    eng = CK.load_checkpoint(str(tmp_path), _FakeEngine, n_images=1, dino_depth=2, siglip_depth=2)
+    # no dataset_statistics.json and no norm_stats in config.json: the reference would fail in _check_unnorm_key
+    with pytest.raises(FileNotFoundError, match="un-normalised"):
+        CK.load_checkpoint(str(tmp_path), _FakeEngine, n_images=1, dino_depth=2, siglip_depth=2)
+    eng = CK.load_checkpoint(str(tmp_path), _FakeEngine, n_images=1, dino_depth=2, siglip_depth=2,
+                             allow_missing_stats=True)
     assert eng.kw["norm_stats"] is None and eng.kw["vocab_size"] == 64
+    # ... but config.json's own norm_stats (what the model carries, MP:738) are the fallback
+    cfg_path = os.path.join(str(tmp_path), "config.json")
+    c = json.load(open(cfg_path))
+    c["norm_stats"] = {"from_config": {"action": {"q01": [0.0] * 7, "q99": [1.0] * 7}}}
+    json.dump(c, open(cfg_path, "w"))
+    eng = CK.load_checkpoint(str(tmp_path), _FakeEngine, n_images=1, dino_depth=2, siglip_depth=2)
+    assert list(eng.kw["norm_stats"]) == ["from_config"]
 
 
 @pytest.mark.gpu

@@ -119,7 +119,7 @@ def test_engine_graph_replay_is_deterministic():
     eng = VLAEngine(n_images=2, dino_depth=3, siglip_depth=3, vocab_size=2048, max_batch=2, max_prompt_len=19)
     eng.load_flat(W)
     eng.finalize()
-    ext, aq = eng._prep(ids, None)
+    ext, aq, _ = eng._prep(ids, None)
     dev = eng.device
     pix_d, ext_d, aq_d, prop_d = pix.to(dev).to(torch.bfloat16).contiguous(), ext.to(dev), aq.to(dev), prop.to(dev).float()
     outs = [eng.predict_device(pix_d, ext_d, aq_d, prop_d)[0].cpu() for _ in range(4)]
@@ -218,14 +218,14 @@ def test_engine_limits_and_bad_inputs():
         eng.predict_action_batch(bad, None, pix, prop)
     a, n = eng.predict_action_batch(ids, None, pix, prop)   # the engine stays usable after a rejected call
     assert np.isfinite(n).all()
-    with pytest.raises(ValueError):                      # padded prompts are not part of the path (reference is bs=1)
-        eng.predict_action_batch(ids, torch.tensor([[1] * 6, [1] * 5 + [0]]), pix, prop)
+    with pytest.raises(ValueError):                      # padding must be on the right (causal attention hides it there)
+        eng.predict_action_batch(ids, torch.tensor([[1] * 6, [0] + [1] * 5]), pix, prop)
     with pytest.raises(ValueError):                      # wrong number of image channels
         eng.predict_action_batch(ids, None, pix[:, :3], prop)
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["libero_base", "libero_pro", "single_image"])
+@pytest.mark.parametrize("name", ["libero_base", "libero_pro", "single_image", "libero_full_pro"])
 def test_engine_matches_reference_golden(name):
     """The CUDA engine against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
     oracle/make_golden.py): un-normalised actions within bf16 path noise of the reference's own bf16 run,
@@ -242,8 +242,8 @@ def test_engine_matches_reference_golden(name):
     pix, ids, prop = O.make_inputs(cfg, B, L, seed=seed)
     ext, labels, mask, aq, _ = tokens.build(ids, None, cfg.action_dim)
     assert np.array_equal(ext.numpy(), g["ref_ext_ids"]) and np.array_equal(mask.numpy(), g["ref_mask"])
-    eng = VLAEngine(n_images=cfg.n_images, pro=cfg.pro, dino_depth=3, siglip_depth=3, vocab_size=2048, max_batch=B,
-                    max_prompt_len=L, norm_stats=STATS)
+    eng = VLAEngine(n_images=cfg.n_images, pro=cfg.pro, dino_depth=cfg.dino_depth, siglip_depth=cfg.siglip_depth,
+                    vocab_size=2048, max_batch=B, max_prompt_len=L, norm_stats=STATS)
     eng.load_flat(W)
     eng.finalize()
     actions, normalized, ha = eng.predict_action_batch(ids, None, pix, prop, unnorm_key="synthetic", return_hidden=True)

@@ -106,7 +106,7 @@ def test_device_call_reports_bad_ids_through_check_errors():
     pix_d, prop_d = pix.to(dev).to(torch.bfloat16).contiguous(), prop.to(dev).float().contiguous()
 
     def run(ids_cpu):
-        ext, aq = eng._prep(ids_cpu, None)
+        ext, aq, _ = eng._prep(ids_cpu, None)
         out = eng.predict_device(pix_d, ext.to(dev), aq.to(dev), prop_d)[0]
         rc = eng.lib.vla_check_errors(eng._h, torch.cuda.current_stream().cuda_stream)
         return out.cpu(), rc
@@ -167,3 +167,77 @@ def test_two_devices_one_process():
     e0.close()
     e1.close()
     assert np.array_equal(n0, n1)
+
+
+@pytest.mark.parametrize("pro,B", [(False, 5), (True, 12)])
+def test_mixed_prompt_lengths_in_one_batch(pro, B):
+    """Per-sample prompt lengths (vla_predict's prompt_len; chat prompts span 40-56 tokens, OU:783): the batch is
+    right-padded, causal attention hides the padding, and every sample must come out exactly as when it runs alone
+    with its own length - and within the usual gate of the oracle run per sample (the reference is bs=1, MP:855)."""
+    cfg = O.OracleConfig(n_images=2, dino_depth=2, siglip_depth=2, vocab_size=1024, pro=pro)
+    W = O.make_weights(cfg, seed=17)
+    lens = [9, 14, 7, 14, 11, 8, 13, 14, 10, 12, 9, 14][:B]
+    Lmax = max(lens)
+    pix, ids, prop = O.make_inputs(cfg, B, Lmax, seed=17)
+    mask = (torch.arange(Lmax)[None] < torch.tensor(lens)[:, None]).long()
+    eng = _engine(cfg, W, B, Lmax)
+    actions, normalized, ha = eng.predict_action_batch(ids, mask, pix, prop, return_hidden=True)
+    # list-of-rows form of the same call
+    _, n_list = eng.predict_action_batch([ids[b, :lens[b]] for b in range(B)], None, pix, prop)
+    assert np.array_equal(n_list, normalized)
+    worst_alone, worst_oracle = 0.0, 0.0
+    for b in range(B):
+        i1 = ids[b:b + 1, :lens[b]]
+        _, n1, h1 = eng.predict_action_batch(i1, None, pix[b:b + 1], prop[b:b + 1], return_hidden=True)
+        worst_alone = max(worst_alone, float(np.abs(n1[0] - normalized[b]).max()))
+        assert torch.equal(h1[0], ha[b]), f"sample {b}: last-layer ActionQuery states differ from the stand-alone run"
+        t = O.predict_action_batch(W, cfg, pix[b:b + 1], i1, prop[b:b + 1], torch.float32)["normalized"].numpy()
+        worst_oracle = max(worst_oracle, float(np.abs(t[0] - normalized[b]).max()))
+    eng.close()
+    print(f"pro={pro} B={B}: max |batched - alone| = {worst_alone:.2e}, max |batched - fp32 oracle| = {worst_oracle:.4f}")
+    assert worst_alone <= 2e-3       # same arithmetic per row; only the batch-size branch (B = 1 vs B) may differ
+    assert worst_oracle <= 3e-2
+    with pytest.raises(ValueError):  # a zero-length prompt
+        eng2 = _engine(cfg, W, 2, 4)
+        try:
+            eng2.predict_action_batch(ids[:2, :4], torch.tensor([[1, 1, 1, 1], [0, 0, 0, 0]]), pix[:2], prop[:2])
+        finally:
+            eng2.close()
+
+
+def test_action_batcher_on_a_real_engine():
+    """SURVEY 8f-3 end to end: concurrent /act-style requests with different prompt lengths share ONE forward of a
+    real engine, and every caller gets the chunk the engine gives that observation alone."""
+    import threading
+
+    from vla_adapter_b200.serving import ActionBatcher
+
+    cfg = O.OracleConfig(n_images=2, dino_depth=2, siglip_depth=2, vocab_size=1024, pro=False)
+    W = O.make_weights(cfg, seed=18)
+    stats = {"k": {"action": {"q01": [-0.5] * 7, "q99": [0.75] * 7, "mask": [True] * 6 + [False]}}}
+    lens = [40, 56, 48, 44, 52, 41]
+    eng = _engine(cfg, W, len(lens), 56, norm_stats=stats)
+    pix, ids, prop = O.make_inputs(cfg, len(lens), 56, seed=18)
+    alone = [eng.predict_action_batch(ids[b:b + 1, :lens[b]], None, pix[b:b + 1], prop[b:b + 1], unnorm_key="k")[0][0]
+             for b in range(len(lens))]
+    batcher = ActionBatcher(eng, max_batch=len(lens), max_wait_ms=500)
+    got, errs = {}, {}
+
+    def go(b):
+        try:
+            got[b] = batcher.submit(ids[b, :lens[b]], pix[b], prop[b].numpy(), "k", timeout=60)
+        except Exception as ex:  # noqa: BLE001
+            errs[b] = ex
+
+    ts = [threading.Thread(target=go, args=(b,)) for b in range(len(lens))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(90)
+    batcher.close()
+    eng.close()
+    assert not errs, errs
+    assert sum(batcher.batches) == len(lens) and max(batcher.batches) >= 2, batcher.batches
+    for b in range(len(lens)):
+        assert got[b].shape == (8, 7) and got[b].dtype == np.float64
+        assert np.abs(got[b] - alone[b]).max() <= 2e-3, b

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from vla_adapter_b200.serving import ActionBatcher
+from vla_adapter_b200.serving import ActionBatcher, TemporalEnsembler
 
 
 class _Engine:
@@ -51,9 +51,65 @@ def test_concurrent_requests_share_a_forward_and_get_their_own_chunk():
     assert b.batches == [4] and eng.calls == [((4, 20), "libero")]
 
 
+def test_mixed_prompt_lengths_share_a_batch():
+    """Chat prompts of 40-56 tokens (OU:783) batch together: right-padded ids + attention mask go to the engine."""
+    seen = {}
+
+    class _E(_Engine):
+        def predict_action_batch(self, input_ids, attention_mask, pixel_values, proprio, unnorm_key=None):
+            seen["mask"] = None if attention_mask is None else attention_mask.clone()
+            seen["ids"] = input_ids.clone()
+            return super().predict_action_batch(input_ids, attention_mask, pixel_values, proprio, unnorm_key)
+
+    eng = _E(delay=0.02)
+    b = ActionBatcher(eng, max_batch=3, max_wait_ms=300)
+    out, errs = _submit_many(b, [(40, "k"), (56, "k"), (48, "k")])
+    b.close()
+    assert not errs and b.batches == [3] and eng.calls == [((3, 56), "k")]
+    for i, a in out.items():
+        assert np.all(a == i)
+    lens = sorted(int(r.sum()) for r in seen["mask"])
+    assert lens == [40, 48, 56]
+    for row, m in zip(seen["ids"], seen["mask"]):
+        n = int(m.sum())
+        assert bool((m[:n] == 1).all()) and bool((m[n:] == 0).all()) and bool((row[n:] == 0).all())
+
+
+def test_temporal_ensembler_reproduces_the_reference_schedule():
+    """evaluate_calvin.py:408-489: three chunks predicted at steps 0, 1, 2 are averaged position-wise over 10 steps."""
+    rng = np.random.default_rng(0)
+    b0, b1, b2 = (rng.normal(size=(8, 7)) for _ in range(3))
+    ens = TemporalEnsembler(8, 7, balancing_factor=None, max_chunks=3)
+    got = []
+    for step in range(10):
+        if step < 3:
+            ens.add((b0, b1, b2)[step])
+        else:
+            ens.step_without_prediction()
+        got.append(ens.action())
+    want = [b0[0], (b0[1] + b1[0]) / 2, (b0[2] + b1[1] + b2[0]) / 3]
+    want += [(b0[t] + b1[t - 1] + b2[t - 2]) / 3 for t in range(3, 8)]       # the reference's t in range(2, 7) loop, +1
+    want += [(b1[7] + b2[6]) / 2, b2[7]]
+    # the reference loops t = 2..6 after its three explicit steps, i.e. chunk positions 3..7 of b0
+    assert len(got) == len(want) == 10
+    for g, w in zip(got, want):
+        assert np.allclose(g, w)
+    # the weighted form of vla_evaluation.py:205-217: newest chunk weighs exp(0), age i weighs exp(-0.1 i)
+    ens = TemporalEnsembler(8, 7)
+    ens.add(b0)
+    ens.add(b1)
+    w = np.exp(-0.1 * np.arange(2))
+    assert np.allclose(ens.action(), (w[0] * b1[0] + w[1] * b0[1]) / w.sum())
+    ens.reset()
+    with pytest.raises(RuntimeError):
+        ens.action()
+    with pytest.raises(ValueError):
+        ens.add(np.zeros((7, 7)))
+
+
 def test_groups_by_prompt_length_and_key_and_caps_batch():
     eng = _Engine(delay=0.01)
-    b = ActionBatcher(eng, max_batch=2, max_wait_ms=100)
+    b = ActionBatcher(eng, max_batch=2, max_wait_ms=100, mix_lengths=False)
     specs = [(20, "a"), (20, "a"), (20, "a"), (31, "a"), (20, "b")]
     out, errs = _submit_many(b, specs)
     b.close()
@@ -76,7 +132,7 @@ def test_lone_request_is_not_held_longer_than_max_wait():
 
 def test_engine_error_reaches_every_caller_of_that_batch_only():
     eng = _Engine(fail_on=31)
-    b = ActionBatcher(eng, max_batch=4, max_wait_ms=50)
+    b = ActionBatcher(eng, max_batch=4, max_wait_ms=50, mix_lengths=False)
     out, errs = _submit_many(b, [(31, None), (31, None), (20, None)])
     b.close()
     assert set(errs) == {0, 1} and all(isinstance(e, ValueError) for e in errs.values())

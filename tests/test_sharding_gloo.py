@@ -31,6 +31,33 @@ def _fake_predict(ids, pix, prop):
     return (s.unsqueeze(-1) * torch.arange(1, 57).view(1, 8, 7)).float()
 
 
+def _worker_failing(rank, world, port, n, ret):
+    """A rank whose `predict` raises must not leave the others blocked in the collective."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        ids = torch.randint(3, 1000, (n, 12), generator=g)
+        pix = torch.randn(n, 12, 8, 8, generator=g)
+        prop = torch.randn(n, 8, generator=g)
+
+        def predict(i, p, q):
+            if rank == 1:
+                raise ValueError("engine rejected the shard")
+            return _fake_predict(i, p, q)
+
+        try:
+            sharding.predict_sharded(predict, ids, pix, prop)
+            ret[rank] = "returned"
+        except ValueError as ex:
+            ret[rank] = "ValueError" if rank == 1 else f"unexpected {ex}"
+        except RuntimeError as ex:
+            ret[rank] = "RuntimeError" if rank == 0 and "rank(s) [1] failed" in str(ex) else f"unexpected {ex}"
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, n, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -49,7 +76,7 @@ def _worker(rank, world, port, n, ret):
         out = sharding.predict_sharded(predict, ids, pix, prop)
         ref = _fake_predict(ids, pix, prop)
         lo, hi = sharding.shard_range(rank, world, n)
-        ok = torch.equal(out, ref) and calls == [hi - lo]
+        ok = torch.equal(out, ref) and calls == ([hi - lo] if hi > lo else [])
         # timing reduction used by bench.py: max over ranks
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -57,6 +84,31 @@ def _worker(rank, world, port, n, ret):
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
+
+
+def _spawn(target, n, world=2):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=target, args=(r, world, port, n, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0, "a rank hung or crashed"
+    return dict(ret)
+
+
+def test_predict_sharded_failure_on_one_rank_reaches_every_rank():
+    assert _spawn(_worker_failing, 6) == {0: "RuntimeError", 1: "ValueError"}
+
+
+def test_predict_sharded_fewer_samples_than_ranks():
+    """n < world: the trailing ranks own no sample; they must skip `predict` and still take part in the gather."""
+    assert _spawn(_worker, 1, world=3) == {0: True, 1: True, 2: True}
+    assert _spawn(_worker, 2, world=3) == {0: True, 1: True, 2: True}
 
 
 @pytest.mark.parametrize("n", [8, 7, 1])

@@ -38,13 +38,13 @@ SIGNATURES = {
     "vla_load_tensor": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int, c_int, C.POINTER(C.c_int64)]),
     "vla_set_action_stats": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint8)]),
     "vla_finalize": (c_int, [c_void_p]),
-    "vla_predict": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+    "vla_predict": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p]),
-    "vla_predict_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+    "vla_predict_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
-    "vla_predict_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+    "vla_predict_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
-    "vla_predict_host_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+    "vla_predict_host_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
     "vla_set_image_norm": (c_int, [c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vla_segment_timing": (c_int, [c_void_p, c_int]),

@@ -13,6 +13,7 @@ the discarded last ViT block) are skipped by the engine itself.
 """
 from __future__ import annotations
 
+import itertools
 import json
 import os
 from typing import Any, Callable, Dict, Iterator, Optional, Tuple
@@ -74,11 +75,20 @@ def read_config(ckpt_dir: str) -> Dict[str, Any]:
 
 
 def load_norm_stats(ckpt_dir: str) -> Optional[Dict[str, Any]]:
+    """dataset_statistics.json when the directory has one (openvla_utils.py:371-390 overwrites vla.norm_stats with
+    it), else the `norm_stats` entry of config.json, which is what the model itself carries
+    (modeling_prismatic.py:738: `self.norm_stats = config.norm_stats`)."""
     p = os.path.join(ckpt_dir, "dataset_statistics.json")
-    if not os.path.isfile(p):
-        return None
-    with open(p) as f:
-        return json.load(f)
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f)
+    c = os.path.join(ckpt_dir, "config.json")
+    if os.path.isfile(c):
+        with open(c) as f:
+            stats = json.load(f).get("norm_stats")
+        if stats:
+            return stats
+    return None
 
 
 def describe_head(head_sd: Dict[str, torch.Tensor]) -> Dict[str, Any]:
@@ -94,9 +104,11 @@ def describe_head(head_sd: Dict[str, torch.Tensor]) -> Dict[str, Any]:
 
 def load_checkpoint(ckpt_dir: str, engine_factory: Callable[..., Any], n_images: int = 2, chunk_len: int = 8,
                     max_batch: int = 1, max_prompt_len: int = 64, vocab_size: Optional[int] = None,
-                    dino_depth: int = 24, siglip_depth: int = 27, **engine_kw):
+                    dino_depth: int = 24, siglip_depth: int = 27, allow_missing_stats: bool = False, **engine_kw):
     """Builds and finalizes an engine from `ckpt_dir`.  `engine_factory` is VLAEngine (injected so that the host
-    logic can be tested without a GPU).  The embedding table size is read from the checkpoint itself."""
+    logic can be tested without a GPU).  The embedding table size is read from the checkpoint itself.  A directory
+    without un-normalisation statistics is an error (the reference fails in _check_unnorm_key, MP:980-990) unless
+    `allow_missing_stats` is set, in which case the engine returns NORMALISED actions."""
     head_sd = strip_module_prefix(torch.load(find_checkpoint_file(ckpt_dir, "action_head"), map_location="cpu",
                                              weights_only=True))
     prop_sd = strip_module_prefix(torch.load(find_checkpoint_file(ckpt_dir, "proprio_projector"), map_location="cpu",
@@ -114,12 +126,17 @@ def load_checkpoint(ckpt_dir: str, engine_factory: Callable[..., Any], n_images:
                 break
         if vocab_size is None:
             vocab_size = shape["vocab_size"]
+    norm_stats = load_norm_stats(ckpt_dir)
+    if norm_stats is None and not allow_missing_stats:
+        raise FileNotFoundError(
+            f"no dataset_statistics.json and no norm_stats in config.json under {ckpt_dir}: actions could not be "
+            "un-normalised (pass allow_missing_stats=True to get normalised actions)")
     eng = engine_factory(n_images=n_images, chunk_len=chunk_len, action_dim=hd["action_dim"], proprio_dim=proprio_dim,
                          pro=hd["pro"], dino_depth=dino_depth, siglip_depth=siglip_depth, llm_layers=shape["llm_layers"],
                          vocab_size=vocab_size, max_batch=max_batch, max_prompt_len=max_prompt_len,
-                         norm_stats=load_norm_stats(ckpt_dir), **engine_kw)
+                         norm_stats=norm_stats, **engine_kw)
     n = 0
-    for name, t in list(pending) + list(vla_iter):
+    for name, t in itertools.chain(pending, vla_iter):  # streamed: one tensor in host memory at a time
         if torch.is_tensor(t) and t.is_floating_point():
             eng.load_tensor("vla." + name, t)
             n += 1

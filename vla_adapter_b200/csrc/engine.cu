@@ -141,6 +141,9 @@ struct vla_engine {
   std::vector<bf16*> hid;  // 25 LLM states
   bf16 *l_tmp, *l_xn, *l_qkv, *l_attn, *l_act;
   bf16 *h_p1, *h_p, *h_kv, *h_q, *h_ao, *h_y, *h_yn;
+  // prompts of different lengths in one batch (vla_predict's prompt_len): the 64 h_a rows of every sample are gathered
+  // into a dense buffer per policy block, because their row offset then differs from sample to sample
+  std::vector<bf16*> h_ha;
   // small-batch mode (B <= small_B): every policy block has its own K|V buffer so that the K|V projections of the
   // LLM states run on a side stream as soon as each LLM layer finishes, off the policy's critical path
   int small_B = 0;
@@ -155,7 +158,7 @@ struct vla_engine {
        *pin_ha = nullptr;
   void *pin_u8 = nullptr, *dev_u8 = nullptr;
   void *dev_pix = nullptr, *dev_ids = nullptr, *dev_aq = nullptr, *dev_prop = nullptr, *dev_out = nullptr,
-       *dev_ha = nullptr;
+       *dev_ha = nullptr, *dev_len = nullptr;
 
   // last call
   int lastB = 0, lastL = 0;
@@ -166,10 +169,10 @@ struct vla_engine {
   // stream fenced to the caller's stream with events, so the legacy default stream works too.
   struct GraphKey {
     int B, L, u8;
-    const void *pix, *ids, *aq, *prop, *out_norm, *out_unnorm, *out_ha;
+    const void *pix, *ids, *aq, *prop, *len, *out_norm, *out_unnorm, *out_ha;
     bool operator==(const GraphKey& o) const {
       return B == o.B && L == o.L && u8 == o.u8 && pix == o.pix && ids == o.ids && aq == o.aq && prop == o.prop &&
-             out_norm == o.out_norm && out_unnorm == o.out_unnorm && out_ha == o.out_ha;
+             len == o.len && out_norm == o.out_norm && out_unnorm == o.out_unnorm && out_ha == o.out_ha;
     }
   };
   struct GraphEntry {
@@ -424,14 +427,22 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
 // K|V projections of one policy block that depend only on LLM hidden state i+1: the 64 ActionQuery rows -> kv rows
 // [T, T+64) and the NP raw rows -> kv rows [T+65, NK), K columns of the latter scaled by tanh(gating_factor)
 // (AH:269 / AH:391).
-int policy_kv_gemms(vla_engine* e, int i, const bf16* hs, int B, int L, bf16* kvb, cudaStream_t s) {
+int policy_kv_gemms(vla_engine* e, int i, const bf16* hs, int B, int L, const int32_t* prompt_len, bf16* kvb,
+                    cudaStream_t s) {
   const int NP = e->NP, T = e->T;
   const int S = NP + L + N_AQ + 1;
   const int ha_row0 = NP + L - 1;  // MP:855 with NUM_PROMPT_TOKENS = L-1 (MP:927)
   const long long kv_bs = static_cast<long long>(T + N_AQ + 1 + NP) * PKV;
   const HeadBlock& w = e->head[i];
   vla::GemmArgs g;
-  g.A = hs + static_cast<long long>(ha_row0) * D_LLM; g.a_batch_stride = static_cast<long long>(S) * D_LLM; g.lda = D_LLM;
+  if (prompt_len) {  // per-sample offsets: rows [NP + L_b - 1, NP + L_b + 63) of sample b, gathered first
+    CK(vla::gather_rows_launch(hs, static_cast<long long>(S) * D_LLM, D_LLM, ha_row0, N_AQ, B, D_LLM, e->h_ha[i], s, &_err,
+                               prompt_len, L, e->err_flag));
+    g.A = e->h_ha[i]; g.a_batch_stride = static_cast<long long>(N_AQ) * D_LLM;
+  } else {
+    g.A = hs + static_cast<long long>(ha_row0) * D_LLM; g.a_batch_stride = static_cast<long long>(S) * D_LLM;
+  }
+  g.lda = D_LLM;
   g.rows = N_AQ; g.batches = B; g.W = w.wkv_cond; g.ldw = D_LLM; g.N = PKV; g.K = D_LLM;
   g.C = kvb + static_cast<long long>(T) * PKV; g.c_batch_stride = kv_bs; g.ldc = PKV; g.bias = w.bkv_cond;
   CK(vla::gemm_launch(g, s, &_err));
@@ -446,17 +457,22 @@ int policy_kv_gemms(vla_engine* e, int i, const bf16* hs, int B, int L, bf16* kv
 
 // Small-batch mode: the same projections on the side stream, ordered after LLM layer i by an event on the main stream
 // and announced to the policy loop by ev_kv[i].
-int policy_kv_from_llm(vla_engine* e, int i, const bf16* hs, int B, int L, cudaStream_t s, cudaStream_t s2) {
+int policy_kv_from_llm(vla_engine* e, int i, const bf16* hs, int B, int L, const int32_t* prompt_len, cudaStream_t s,
+                       cudaStream_t s2) {
   if (cudaEventRecord(e->ev_layer[i], s) != cudaSuccess || cudaStreamWaitEvent(s2, e->ev_layer[i], 0) != cudaSuccess)
     return e->fail(VLA_ERR_CUDA, "policy K|V fork failed");
-  const int rc = policy_kv_gemms(e, i, hs, B, L, e->h_kv_blk[i], s2);
+  const int rc = policy_kv_gemms(e, i, hs, B, L, prompt_len, e->h_kv_blk[i], s2);
   if (rc) return rc;
   if (cudaEventRecord(e->ev_kv[i], s2) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V event failed");
   return 0;
 }
 
+// prompt_len (device, nullable): per-sample prompt lengths L_b <= L.  The LLM sequences are then RIGHT-padded to the
+// common length NP + L + 65: sample b holds [tok0 | patches | tok1..tok_{L_b-1} | AQ0..63 | stop | padding].  Causal
+// attention never lets a real row see the padding behind it, so every real row equals the row of the un-padded run;
+// only the policy's h_a window (and the returned last-layer states) sits at a per-sample offset.
 int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t* ext_ids, const int32_t* aq_index, const float* proprio,
-            int B, int L, float* out_norm, float* out_unnorm, bf16* out_last_ha, cudaStream_t s) {
+            const int32_t* prompt_len, int B, int L, float* out_norm, float* out_unnorm, bf16* out_last_ha, cudaStream_t s) {
   const int NP = e->NP, T = e->T, A = e->A, P = e->P;
   vla::PdlScope pdl(B <= 8);  // programmatic dependent launch pays off only when kernels are a few microseconds long
   const int Lext = L + N_AQ + 1;
@@ -552,14 +568,14 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     g.C = xout; g.ldc = D_LLM; g.resid = xout; g.ldr = D_LLM;
     CK(vla::gemm_launch(g, s, &_err));
     if (small && l + 1 < NL) {  // hid[l+1] is final: its policy K|V projections start now, beside the next LLM layer
-      rc = policy_kv_from_llm(e, l, e->hid[l + 1], B, L, s, s2);
+      rc = policy_kv_from_llm(e, l, e->hid[l + 1], B, L, prompt_len, s, s2);
       if (rc) return rc;
     }
   }
   // hidden_states[-1] is the post-final-norm state (HF output_hidden_states semantics)
   CK(vla::rmsnorm_launch(e->l_tmp, M, D_LLM, D_LLM, e->llm_norm, LLM_EPS, e->hid[NL], D_LLM, s, &_err));
   if (small) {
-    rc = policy_kv_from_llm(e, NL - 1, e->hid[NL], B, L, s, s2);
+    rc = policy_kv_from_llm(e, NL - 1, e->hid[NL], B, L, prompt_len, s, s2);
     if (rc) return rc;
   }
 
@@ -588,7 +604,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
       // the LLM-state K|V rows of this block were projected on the side stream (policy_kv_from_llm)
       if (cudaStreamWaitEvent(s, e->ev_kv[i], 0) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V join failed");
     } else {
-      rc = policy_kv_gemms(e, i, hs, B, L, kvb, s);
+      rc = policy_kv_gemms(e, i, hs, B, L, prompt_len, kvb, s);
       if (rc) return rc;
     }
     // K|V of the proprio row -> kv row T+64 (projected up front for all blocks: one row copy per sample here)
@@ -622,7 +638,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
   if (seg) cudaEventRecord(e->seg_ev[3], s);
   if (out_last_ha)
     CK(vla::gather_rows_launch(e->hid[NL], static_cast<long long>(S) * D_LLM, D_LLM, ha_row0, N_AQ, B, D_LLM,
-                               out_last_ha, s, &_err));
+                               out_last_ha, s, &_err, prompt_len, L, e->err_flag));
   return 0;
 }
 
@@ -751,7 +767,7 @@ int vla_finalize(vla_engine* e) {
     e->allocs.resize(mark);
     e->jobs.clear();
     e->dino.blocks.clear(); e->sig.blocks.clear(); e->llm.clear(); e->head.clear();
-    e->hid.clear(); e->head_x.clear(); e->h_kv_blk.clear();
+    e->hid.clear(); e->head_x.clear(); e->h_kv_blk.clear(); e->h_ha.clear();
     e->dev_pix = nullptr;
   };
   try {
@@ -948,6 +964,7 @@ int vla_finalize(vla_engine* e) {
         e->ev_kv.push_back(b);
       }
     }
+    for (int i = 0; i < 24; ++i) e->h_ha.push_back(e->dalloc<bf16>(static_cast<size_t>(B) * N_AQ * D_LLM));
     e->h_pkv = e->dalloc<bf16>(static_cast<size_t>(B) * 24 * PKV);
     e->h_q = e->dalloc<bf16>(BT * D_LLM);
     e->h_ao = e->dalloc<bf16>(BT * D_LLM);
@@ -981,8 +998,8 @@ int vla_finalize(vla_engine* e) {
 }
 
 static int predict_impl(vla_engine* e, const void* pixel_values, int is_u8, const int64_t* ext_ids,
-                        const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm, float* out_unnorm,
-                        void* out_last_ha, void* stream) {
+                        const int32_t* aq_index, const float* proprio, const int32_t* prompt_len, int B, int L,
+                        float* out_norm, float* out_unnorm, void* out_last_ha, void* stream) {
   if (!e) return VLA_ERR_INVALID;
   if (!e->finalized) return e->fail(VLA_ERR_NOT_FINALIZED, "vla_predict before vla_finalize");
   if (!pixel_values || !ext_ids || !aq_index || !proprio || !out_norm)
@@ -997,7 +1014,7 @@ static int predict_impl(vla_engine* e, const void* pixel_values, int is_u8, cons
   int rc = 0;
   vla_engine::GraphEntry* ge = nullptr;
   if (e->use_graphs && !vla::gemm_profile_enabled() && !e->seg_on) {
-    const vla_engine::GraphKey key{B, L, is_u8, pixel_values, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha};
+    const vla_engine::GraphKey key{B, L, is_u8, pixel_values, ext_ids, aq_index, proprio, prompt_len, out_norm, out_unnorm, out_last_ha};
     for (auto& g : e->graphs)
       if (g.key == key) ge = &g;
     if (!ge) {
@@ -1023,7 +1040,7 @@ static int predict_impl(vla_engine* e, const void* pixel_values, int is_u8, cons
       const long long before = vla::gemm_launch_count() + vla::ops_launch_count();
       if (cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
         return e->fail(VLA_ERR_CUDA, "cudaStreamBeginCapture failed");
-      rc = forward(e, pix, pix8, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, ha, e->gstream);
+      rc = forward(e, pix, pix8, ext_ids, aq_index, proprio, prompt_len, B, L, out_norm, out_unnorm, ha, e->gstream);
       const cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
       ge->launches = vla::gemm_launch_count() + vla::ops_launch_count() - before;
       if (rc) {
@@ -1044,7 +1061,7 @@ static int predict_impl(vla_engine* e, const void* pixel_values, int is_u8, cons
     e->last_launches = ge->launches;
   } else {
     const long long before = vla::gemm_launch_count() + vla::ops_launch_count();
-    rc = forward(e, pix, pix8, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, ha, s);
+    rc = forward(e, pix, pix8, ext_ids, aq_index, proprio, prompt_len, B, L, out_norm, out_unnorm, ha, s);
     e->last_launches = vla::gemm_launch_count() + vla::ops_launch_count() - before;
   }
   e->lastB = B;
@@ -1053,15 +1070,16 @@ static int predict_impl(vla_engine* e, const void* pixel_values, int is_u8, cons
 }
 
 int vla_predict(vla_engine* e, const void* pixel_values, const int64_t* ext_ids, const int32_t* aq_index,
-                const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
-                void* stream) {
-  return predict_impl(e, pixel_values, 0, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, out_last_ha, stream);
+                const int32_t* prompt_len, const float* proprio, int B, int L, float* out_norm, float* out_unnorm,
+                void* out_last_ha, void* stream) {
+  return predict_impl(e, pixel_values, 0, ext_ids, aq_index, proprio, prompt_len, B, L, out_norm, out_unnorm, out_last_ha,
+                      stream);
 }
 
 int vla_predict_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids, const int32_t* aq_index,
-                   const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
-                   void* stream) {
-  return predict_impl(e, images, 1, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, out_last_ha, stream);
+                   const int32_t* prompt_len, const float* proprio, int B, int L, float* out_norm, float* out_unnorm,
+                   void* out_last_ha, void* stream) {
+  return predict_impl(e, images, 1, ext_ids, aq_index, proprio, prompt_len, B, L, out_norm, out_unnorm, out_last_ha, stream);
 }
 
 int vla_set_image_norm(vla_engine* e, const float* mean, const float* stdv) {
@@ -1091,8 +1109,8 @@ int vla_set_image_norm(vla_engine* e, const float* mean, const float* stdv) {
 }
 
 static int predict_host_impl(vla_engine* e, const void* pixel_values, int is_u8, const int64_t* ext_ids,
-                             const int32_t* aq_index, const float* proprio, int B, int L, float* out_norm,
-                             float* out_unnorm, void* out_last_ha, void* stream) {
+                             const int32_t* aq_index, const int32_t* prompt_len, const float* proprio, int B, int L,
+                             float* out_norm, float* out_unnorm, void* out_last_ha, void* stream) {
   if (!e) return VLA_ERR_INVALID;
   if (!e->finalized) return e->fail(VLA_ERR_NOT_FINALIZED, "vla_predict_host before vla_finalize");
   if (!pixel_values || !ext_ids || !aq_index || !proprio || !out_norm)
@@ -1113,6 +1131,7 @@ static int predict_host_impl(vla_engine* e, const void* pixel_values, int is_u8,
       e->dev_ids = e->dalloc<uint8_t>(ids_b);
       e->dev_aq = e->dalloc<uint8_t>(aq_b);
       e->dev_prop = e->dalloc<uint8_t>(prop_b);
+      e->dev_len = e->dalloc<uint8_t>(static_cast<size_t>(e->maxB) * 4);
       e->dev_out = e->dalloc<uint8_t>(2 * out_b);
       e->dev_ha = e->dalloc<uint8_t>(ha_b);
     } catch (const std::exception& ex) {
@@ -1129,11 +1148,18 @@ static int predict_host_impl(vla_engine* e, const void* pixel_values, int is_u8,
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_ids, ext_ids, static_cast<size_t>(B) * Lext * 8, cudaMemcpyHostToDevice, s);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_aq, aq_index, static_cast<size_t>(B) * Lext * 4, cudaMemcpyHostToDevice, s);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_prop, proprio, static_cast<size_t>(B) * e->P * 4, cudaMemcpyHostToDevice, s);
+  if (prompt_len) {  // host array: validated here, so a bad length never reaches the device
+    for (int b = 0; b < B; ++b)
+      if (prompt_len[b] < 1 || prompt_len[b] > L)
+        return e->fail(VLA_ERR_INVALID, "vla_predict_host: prompt_len[" + std::to_string(b) + "] outside [1, L]");
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->dev_len, prompt_len, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s);
+  }
   if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(ce));
   float* d_norm = static_cast<float*>(e->dev_out);
   float* d_un = d_norm + static_cast<size_t>(e->maxB) * e->T * e->A;
   int rc = predict_impl(e, e->dev_pix, is_u8, static_cast<const int64_t*>(e->dev_ids), static_cast<const int32_t*>(e->dev_aq),
-                       static_cast<const float*>(e->dev_prop), B, L, d_norm, d_un, out_last_ha ? e->dev_ha : nullptr, stream);
+                       static_cast<const float*>(e->dev_prop), prompt_len ? static_cast<const int32_t*>(e->dev_len) : nullptr,
+                       B, L, d_norm, d_un, out_last_ha ? e->dev_ha : nullptr, stream);
   if (rc) return rc;
   ce = cudaMemcpyAsync(out_norm, d_norm, n_out * 4, cudaMemcpyDeviceToHost, s);
   if (ce == cudaSuccess && out_unnorm) ce = cudaMemcpyAsync(out_unnorm, d_un, n_out * 4, cudaMemcpyDeviceToHost, s);
@@ -1145,21 +1171,24 @@ static int predict_host_impl(vla_engine* e, const void* pixel_values, int is_u8,
   if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("predict: ") + cudaGetErrorString(ce));
   if (flag) {
     cudaMemset(e->err_flag, 0, sizeof(int));
-    return e->fail(VLA_ERR_INVALID, flag == 1 ? "token id outside [0, vocab_size)" : "ActionQuery index outside [0, 64)");
+    return e->fail(VLA_ERR_INVALID, flag == 1 ? "token id outside [0, vocab_size)"
+                                    : (flag == 2 ? "ActionQuery index outside [0, 64)" : "prompt length outside [1, L]"));
   }
   return VLA_OK;
 }
 
 int vla_predict_host(vla_engine* e, const void* pixel_values, const int64_t* ext_ids, const int32_t* aq_index,
-                     const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
-                     void* stream) {
-  return predict_host_impl(e, pixel_values, 0, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, out_last_ha, stream);
+                     const int32_t* prompt_len, const float* proprio, int B, int L, float* out_norm, float* out_unnorm,
+                     void* out_last_ha, void* stream) {
+  return predict_host_impl(e, pixel_values, 0, ext_ids, aq_index, prompt_len, proprio, B, L, out_norm, out_unnorm,
+                           out_last_ha, stream);
 }
 
 int vla_predict_host_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids, const int32_t* aq_index,
-                        const float* proprio, int B, int L, float* out_norm, float* out_unnorm, void* out_last_ha,
-                        void* stream) {
-  return predict_host_impl(e, images, 1, ext_ids, aq_index, proprio, B, L, out_norm, out_unnorm, out_last_ha, stream);
+                        const int32_t* prompt_len, const float* proprio, int B, int L, float* out_norm,
+                        float* out_unnorm, void* out_last_ha, void* stream) {
+  return predict_host_impl(e, images, 1, ext_ids, aq_index, prompt_len, proprio, B, L, out_norm, out_unnorm, out_last_ha,
+                           stream);
 }
 
 int vla_get_tap(vla_engine* e, const char* name, void* dst, size_t capacity, size_t* bytes) {
@@ -1234,7 +1263,8 @@ int vla_check_errors(vla_engine* e, void* stream) {
   if (ce != cudaSuccess) return e->fail(VLA_ERR_CUDA, std::string("forward failed: ") + cudaGetErrorString(ce));
   if (flag) {
     cudaMemsetAsync(e->err_flag, 0, sizeof(int), s);
-    return e->fail(VLA_ERR_INVALID, flag == 1 ? "token id outside [0, vocab_size)" : "ActionQuery index outside [0, 64)");
+    return e->fail(VLA_ERR_INVALID, flag == 1 ? "token id outside [0, vocab_size)"
+                                    : (flag == 2 ? "ActionQuery index outside [0, 64)" : "prompt length outside [1, L]"));
   }
   return VLA_OK;
 }

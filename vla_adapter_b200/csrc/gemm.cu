@@ -61,6 +61,9 @@ struct GemmDev {
   int rope_cols, rope_S, rope_ld;
   const float2* row_stats;  // normalisation of A folded into the epilogue (see GemmArgs)
   const float* colsum;
+  // profiling only (vla_profile_gemm): CTA 0's monitor warp writes {globaltimer, clock64} at its start and end, which
+  // gives the kernel's duration AND the SM clock it ran at inside a real step (ncu serialises and cannot show that)
+  unsigned long long* prof;
 };
 
 VLA_DEVINL void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
@@ -250,9 +253,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     }
   } else if (warp_idx == GEMM_WORK_WARPS) {
     // ------------------------------------------------------------ watchdog monitor (see common.cuh)
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && lane == 0;
+    if (prof) {
+      p.prof[0] = global_timer_ns();
+      p.prof[1] = static_cast<unsigned long long>(clock64());
+    }
     wd_monitor(done_bar, note_base, GEMM_WORK_WARPS, CG == 2 ? WD_K_GEMM2 : WD_K_GEMM1, [&](uint32_t kind, uint32_t idx) {
       return kind == 1 ? empty_bar(idx) : kind == 2 ? full_bar(idx) : kind == 3 ? tempty_bar(idx) : kind == 4 ? tfull_bar(idx) : 0u;
     });
+    if (prof) {
+      p.prof[2] = global_timer_ns();
+      p.prof[3] = static_cast<unsigned long long>(clock64());
+    }
   } else {
     // ------------------------------------------------------------ epilogue: 8 warps, each 32 rows x bn/2 columns
     const int e = warp_idx - 2;
@@ -526,7 +538,10 @@ std::atomic<long long> g_launches{0};
 struct ProfRec {
   cudaEvent_t e0, e1;
   int rows, batches, N, K, bn, act;
+  int slot;  // index into g_prof_dev (4 words per launch), -1 = none
 };
+constexpr int PROF_SLOTS = 8192;
+unsigned long long* g_prof_dev = nullptr;
 FILE* g_prof_csv = nullptr;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
@@ -579,14 +594,29 @@ void gemm_profile_enable(bool on) {
 int gemm_profile_read(double* total_ms, long long* launches) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   double tot = 0.0;
+  std::vector<unsigned long long> dev(g_prof.size() * 4, 0ull);
+  if (g_prof_dev && !g_prof.empty()) {
+    cudaDeviceSynchronize();
+    const size_t n = g_prof.size() < static_cast<size_t>(PROF_SLOTS) ? g_prof.size() : static_cast<size_t>(PROF_SLOTS);
+    cudaMemcpy(dev.data(), g_prof_dev, n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  }
   for (auto& r : g_prof) {
     cudaEventSynchronize(r.e1);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) tot += ms;
     if (g_prof_csv) {
+      // columns: rows,batches,N,K,bn,act, event ms, TFLOP/s, CTA-0 lifetime [us] and the SM clock [MHz] it ran at
       const double fl = 2.0 * r.rows * r.batches * r.N * r.K;
-      fprintf(g_prof_csv, "%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.rows, r.batches, r.N, r.K, r.bn, r.act, ms,
-              fl / (ms * 1e-3) / 1e12);
+      double us = 0.0, mhz = 0.0;
+      if (r.slot >= 0) {
+        const unsigned long long* d = dev.data() + 4 * r.slot;
+        if (d[2] > d[0]) {
+          us = (d[2] - d[0]) * 1e-3;
+          mhz = static_cast<double>(d[3] - d[1]) / us;
+        }
+      }
+      fprintf(g_prof_csv, "%d,%d,%d,%d,%d,%d,%.5f,%.1f,%.2f,%.0f\n", r.rows, r.batches, r.N, r.K, r.bn, r.act, ms,
+              fl / (ms * 1e-3) / 1e12, us, mhz);
     }
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -728,6 +758,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.rope_ld = a.rope_ld > 0 ? a.rope_ld : a.rope_S;
   p.row_stats = reinterpret_cast<const float2*>(a.row_stats);
   p.colsum = a.colsum;
+  p.prof = nullptr;
 
   CUtensorMap mA, mB, mC;
   const uint64_t a_bs = a.batches > 1 ? static_cast<uint64_t>(a.a_batch_stride)
@@ -752,7 +783,17 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   ProfRec rec{};
   rec.rows = p.rows; rec.batches = p.batches; rec.N = p.N; rec.K = p.K; rec.bn = bn; rec.act = p.act;
   const bool prof = g_prof_on;
+  rec.slot = -1;
   if (prof) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_dev && cudaMalloc(&g_prof_dev, PROF_SLOTS * 4 * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaGetLastError();
+      g_prof_dev = nullptr;
+    }
+    if (g_prof_dev && g_prof.size() < static_cast<size_t>(PROF_SLOTS)) {
+      rec.slot = static_cast<int>(g_prof.size());
+      p.prof = g_prof_dev + 4 * rec.slot;
+    }
     cudaEventCreate(&rec.e0);
     cudaEventCreate(&rec.e1);
     cudaEventRecord(rec.e0, stream);

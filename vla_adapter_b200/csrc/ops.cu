@@ -438,8 +438,12 @@ skinny_linear_kernel(const void* __restrict__ x, int x_is_f32, int ldx, int M, i
   }
 }
 
+// dst[b, r, :] = src[b, r0 + (len ? len[b] - len_ref : 0) + r, :]: rows [r0, r0 + rows) of every slab, shifted per
+// slab when the samples' prompts have different lengths (len_ref = the length r0 was computed for; a length outside
+// [1, len_ref] raises error flag 3 and reads as len_ref).
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long src_bs, int ld, int r0,
-                                   int rows, int batches, int dim, __nv_bfloat16* __restrict__ dst) {
+                                   int rows, int batches, int dim, __nv_bfloat16* __restrict__ dst,
+                                   const int32_t* __restrict__ len, int len_ref, int* err_flag) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
   pdl_launch_dependents();
   const int nvec = dim >> 3;
@@ -450,8 +454,17 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long l
   const long long t = idx / nvec;
   const int r = static_cast<int>(t % rows);
   const long long b = t / rows;
+  int shift = 0;
+  if (len) {
+    const int l = len[b];
+    if (l < 1 || l > len_ref) {
+      if (err_flag && v == 0 && r == 0) atomicExch(err_flag, 3);
+    } else {
+      shift = l - len_ref;
+    }
+  }
   reinterpret_cast<uint4*>(dst)[idx] =
-      *reinterpret_cast<const uint4*>(src + b * src_bs + static_cast<long long>(r0 + r) * ld + v * 8);
+      *reinterpret_cast<const uint4*>(src + b * src_bs + static_cast<long long>(r0 + shift + r) * ld + v * 8);
 }
 
 __global__ void broadcast_row_kernel(const __nv_bfloat16* __restrict__ src, int dim, int rows,
@@ -608,10 +621,11 @@ int broadcast_row_launch(const __nv_bfloat16* src, int dim, int rows, __nv_bfloa
 }
 
 int gather_rows_launch(const __nv_bfloat16* src, long long src_bs, int ld, int r0, int rows, int batches,
-                       int dim, __nv_bfloat16* dst, cudaStream_t s, const char** err) {
+                       int dim, __nv_bfloat16* dst, cudaStream_t s, const char** err, const int32_t* len, int len_ref,
+                       int* err_flag) {
   const long long total = static_cast<long long>(batches) * rows * (dim >> 3);
   launch_kernel(gather_rows_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, src, src_bs, ld, r0, rows, batches,
-                                                                          dim, dst);
+                                                                          dim, dst, len, len_ref, err_flag);
   return check_launch(err);
 }
 

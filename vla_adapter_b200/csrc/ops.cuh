@@ -107,8 +107,11 @@ int policy_rope_table_launch(float* cos_t, float* sin_t, int max_pos, cudaStream
 int broadcast_row_launch(const __nv_bfloat16* src, int dim, int rows, __nv_bfloat16* dst, cudaStream_t s,
                          const char** err);
 
-// Copies rows [r0, r0+rows) of every slab into a dense buffer (tap extraction).
+// Copies rows [r0, r0+rows) of every slab into a dense buffer (tap extraction).  With `len` (device, one prompt length
+// per slab) the window of slab b is shifted by len[b] - len_ref: samples whose prompts have different lengths keep their
+// ActionQuery rows at different offsets of the (right-padded) LLM sequence.
 int gather_rows_launch(const __nv_bfloat16* src, long long src_bs, int ld, int r0, int rows, int batches,
-                       int dim, __nv_bfloat16* dst, cudaStream_t s, const char** err);
+                       int dim, __nv_bfloat16* dst, cudaStream_t s, const char** err, const int32_t* len = nullptr,
+                       int len_ref = 0, int* err_flag = nullptr);
 
 }  // namespace vla

@@ -161,16 +161,46 @@ class VLAEngine:
 
     # ------------------------------------------------------------------ forward
     def _prep(self, input_ids, attention_mask):
-        if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
-            raise ValueError("padded prompts are not supported: group samples by prompt length")
-        ids = torch.as_tensor(input_ids).to("cpu", torch.int64)
-        ext, labels, mask, aq_index, _ = tokens.build(ids, None, self.action_dim)
-        return ext.contiguous(), aq_index.contiguous()
+        """-> (ext_ids (B, L+65) int64, aq_index (B, L+65) int32, prompt_len (B) int32 or None).
+
+        Prompts of different lengths come RIGHT-padded with their attention mask (rows of ones followed by zeros, the
+        tokenizer's padding_side="right"), or as a list of 1-D id tensors.  Every sample gets the reference's own bs=1
+        preamble (tokens.build on its un-padded ids, MP:922-937) and the result is padded on the right, where causal
+        attention cannot see it; `prompt_len` tells the engine where each sample's ActionQuery rows sit."""
+        if isinstance(input_ids, (list, tuple)) and len(input_ids) and torch.as_tensor(input_ids[0]).dim() == 1:
+            rows = [torch.as_tensor(r).to("cpu", torch.int64) for r in input_ids]
+        else:
+            ids = torch.as_tensor(input_ids).to("cpu", torch.int64)
+            if ids.dim() != 2:
+                raise ValueError("input_ids must be (B, L)")
+            if attention_mask is None or bool(torch.as_tensor(attention_mask).bool().all()):
+                ext, labels, mask, aq_index, _ = tokens.build(ids, None, self.action_dim)
+                return ext.contiguous(), aq_index.contiguous(), None
+            am = torch.as_tensor(attention_mask).to("cpu").bool()
+            if am.shape != ids.shape:
+                raise ValueError("attention_mask must have the shape of input_ids")
+            lens = am.sum(1)
+            if bool((lens < 1).any()) or not bool((am == (torch.arange(ids.shape[1])[None] < lens[:, None])).all()):
+                raise ValueError("padded prompts must be right-padded (mask = ones then zeros) and non-empty")
+            rows = [ids[b, : int(lens[b])] for b in range(ids.shape[0])]
+        L = max(int(r.numel()) for r in rows)
+        if min(int(r.numel()) for r in rows) < 1:
+            raise ValueError("empty prompt")
+        ext = torch.zeros((len(rows), L + NUM_TOKENS + 1), dtype=torch.int64)   # pad id 0: any valid id will do
+        aq = torch.full((len(rows), L + NUM_TOKENS + 1), -1, dtype=torch.int32)
+        for b, r in enumerate(rows):
+            e1, _, _, a1, _ = tokens.build(r[None], None, self.action_dim)
+            ext[b, : e1.shape[1]] = e1[0]
+            aq[b, : a1.shape[1]] = a1[0]
+        lens = torch.tensor([int(r.numel()) for r in rows], dtype=torch.int32)
+        if bool((lens == L).all()):
+            return ext, aq, None
+        return ext, aq, lens
 
     def predict_device(self, pixel_values: torch.Tensor, ext_ids: torch.Tensor, aq_index: torch.Tensor,
-                       proprio: torch.Tensor, want_last_ha: bool = False):
-        """Inputs already on the device (bf16 pixels, int64 ids, int32 indices, fp32 proprio); enqueues on the
-        current stream and returns device tensors (normalized, unnormalized[, last_ha])."""
+                       proprio: torch.Tensor, want_last_ha: bool = False, prompt_len: Optional[torch.Tensor] = None):
+        """Inputs already on the device (bf16 pixels, int64 ids, int32 indices, fp32 proprio[, int32 prompt lengths]);
+        enqueues on the current stream and returns device tensors (normalized, unnormalized[, last_ha])."""
         B, Lext = ext_ids.shape
         L = Lext - NUM_TOKENS - 1
         T, A = self.chunk_len, self.action_dim
@@ -185,6 +215,9 @@ class VLAEngine:
                                  f"{tuple(t.shape)} on {t.device}")
         if not pixel_values.is_cuda:
             raise ValueError("predict_device takes CUDA tensors (use predict_host for host buffers)")
+        if prompt_len is not None and (prompt_len.dtype != torch.int32 or tuple(prompt_len.shape) != (B,) or
+                                       not prompt_len.is_cuda or not prompt_len.is_contiguous()):
+            raise ValueError(f"prompt_len must be a contiguous CUDA int32 tensor of shape ({B},)")
         # The engine replays a CUDA graph keyed on (B, L, buffer addresses): write into buffers that stay put and
         # hand fresh copies (a few hundred bytes per sample) to the caller.
         key = (B, want_last_ha)
@@ -197,6 +230,7 @@ class VLAEngine:
             self._out_bufs[key] = bufs
         out_n, out_u, ha = bufs
         rc = self.lib.vla_predict(self._h, pixel_values.data_ptr(), ext_ids.data_ptr(), aq_index.data_ptr(),
+                                  prompt_len.data_ptr() if prompt_len is not None else None,
                                   proprio.data_ptr(), B, L, out_n.data_ptr(), out_u.data_ptr(),
                                   ha.data_ptr() if ha is not None else None,
                                   torch.cuda.current_stream().cuda_stream)
@@ -205,15 +239,16 @@ class VLAEngine:
 
     def predict_host(self, pixel_values: torch.Tensor, ext_ids: torch.Tensor, aq_index: torch.Tensor,
                      proprio: torch.Tensor, out_norm: torch.Tensor, out_unnorm: torch.Tensor,
-                     out_last_ha: Optional[torch.Tensor] = None) -> None:
+                     out_last_ha: Optional[torch.Tensor] = None, prompt_len: Optional[torch.Tensor] = None) -> None:
         """End-to-end call on HOST tensors (ideally pinned): H2D, forward, D2H, stream sync inside."""
         B, Lext = ext_ids.shape
         if pixel_values.dtype != torch.bfloat16 or tuple(pixel_values.shape) != (B, 6 * self.n_images, 224, 224):
             raise ValueError(f"pixel_values must be bf16 ({B}, {6 * self.n_images}, 224, 224), got {pixel_values.dtype} "
                              f"{tuple(pixel_values.shape)}")
-        self._check_host_io(B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha)
+        self._check_host_io(B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha, prompt_len)
         pixel_values = pixel_values.contiguous()
         rc = self.lib.vla_predict_host(self._h, pixel_values.data_ptr(), ext_ids.data_ptr(), aq_index.data_ptr(),
+                                       prompt_len.data_ptr() if prompt_len is not None else None,
                                        proprio.data_ptr(), B, Lext - NUM_TOKENS - 1, out_norm.data_ptr(),
                                        out_unnorm.data_ptr(),
                                        out_last_ha.data_ptr() if out_last_ha is not None else None,
@@ -222,23 +257,25 @@ class VLAEngine:
 
     def predict_host_u8(self, images_u8: torch.Tensor, ext_ids: torch.Tensor, aq_index: torch.Tensor,
                         proprio: torch.Tensor, out_norm: torch.Tensor, out_unnorm: torch.Tensor,
-                        out_last_ha: Optional[torch.Tensor] = None) -> None:
+                        out_last_ha: Optional[torch.Tensor] = None, prompt_len: Optional[torch.Tensor] = None) -> None:
         """predict_host from uint8 frames (B, n_images, 224, 224, 3), HWC, already resized / centre-cropped: the
         processor's ToTensor + Normalize + bf16 cast happen on the device (bit-identical to the CPU path)."""
         B, Lext = ext_ids.shape
         if images_u8.dtype != torch.uint8 or tuple(images_u8.shape) != (B, self.n_images, 224, 224, 3):
             raise ValueError(f"images must be uint8 ({B}, {self.n_images}, 224, 224, 3), got {images_u8.dtype} "
                              f"{tuple(images_u8.shape)}")
-        self._check_host_io(B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha)
+        self._check_host_io(B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha, prompt_len)
         images_u8 = images_u8.contiguous()
         rc = self.lib.vla_predict_host_u8(self._h, images_u8.data_ptr(), ext_ids.data_ptr(), aq_index.data_ptr(),
+                                          prompt_len.data_ptr() if prompt_len is not None else None,
                                           proprio.data_ptr(), B, Lext - NUM_TOKENS - 1, out_norm.data_ptr(),
                                           out_unnorm.data_ptr(),
                                           out_last_ha.data_ptr() if out_last_ha is not None else None,
                                           torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, self._h)
 
-    def _check_host_io(self, B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha) -> None:
+    def _check_host_io(self, B, Lext, ext_ids, aq_index, proprio, out_norm, out_unnorm, out_last_ha,
+                       prompt_len=None) -> None:
         """The C ABI takes raw pointers: every buffer it will read or write is checked here for dtype, size and
         contiguity (the reference raises on mismatched batches, MP:519-522)."""
         T, A = self.chunk_len, self.action_dim
@@ -255,6 +292,8 @@ class VLAEngine:
         need("out_unnorm", out_unnorm, torch.float32, (B, T, A))
         if out_last_ha is not None:
             need("out_last_ha", out_last_ha, torch.bfloat16, (B, NUM_TOKENS, LLM_DIM))
+        if prompt_len is not None:
+            need("prompt_len", prompt_len, torch.int32, (B,))
 
     def set_image_norm(self, mean, std) -> None:
         """mean / std of the two backbones, each (2, 3): row 0 DINOv2, row 1 SigLIP (preprocessor_config.json)."""
@@ -269,7 +308,7 @@ class VLAEngine:
         and normalised actions (B, T, A) float32 [+ last-layer ActionQuery states (B, 1, 64, D) bf16]."""
         if not self._finalized:
             raise RuntimeError("engine not finalized")
-        ext, aq = self._prep(input_ids, attention_mask)
+        ext, aq, lens = self._prep(input_ids, attention_mask)
         B = ext.shape[0]
         if (pixel_values is None) == (images_u8 is None):
             raise ValueError("pass exactly one of pixel_values (normalised, like the reference) or images_u8")
@@ -282,19 +321,23 @@ class VLAEngine:
         pr = pr.reshape(B, -1).contiguous()
         if pr.shape[1] != self.proprio_dim:
             raise ValueError(f"proprio must have {self.proprio_dim} dims per sample")
-        self._push_stats(unnorm_key) if self.norm_stats is not None else None
+        if self.norm_stats is not None:
+            self._push_stats(unnorm_key)
+        elif unnorm_key is not None:
+            # the reference would fail in _check_unnorm_key (MP:980-990): there is nothing to look the key up in
+            raise ValueError(f"unnorm_key={unnorm_key!r} given but the engine has no normalisation statistics")
         T, A = self.chunk_len, self.action_dim
         out_n = torch.empty((B, T, A), dtype=torch.float32)
         out_u = torch.empty((B, T, A), dtype=torch.float32)
         ha = torch.empty((B, NUM_TOKENS, LLM_DIM), dtype=torch.bfloat16) if return_hidden else None
         if images_u8 is None:
-            self.predict_host(pix.cpu(), ext, aq, pr, out_n, out_u, ha)
+            self.predict_host(pix.cpu(), ext, aq, pr, out_n, out_u, ha, lens)
         else:
-            self.predict_host_u8(pix.cpu(), ext, aq, pr, out_n, out_u, ha)
+            self.predict_host_u8(pix.cpu(), ext, aq, pr, out_n, out_u, ha, lens)
         normalized = out_n.numpy()
         if self.norm_stats is not None:
             actions = self._unnormalize_actions(normalized.astype(np.float32), unnorm_key)
-        else:
+        else:  # no statistics: the engine's table is the identity (hi = 1, lo = -1): NORMALISED actions come back
             actions = out_u.numpy().astype(np.float64)
         if return_hidden:
             return actions, normalized, ha.view(B, 1, NUM_TOKENS, LLM_DIM)

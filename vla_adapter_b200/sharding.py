@@ -68,5 +68,46 @@ def predict_sharded(predict: Callable[..., torch.Tensor], input_ids: torch.Tenso
     if pixel_values.shape[0] != n or proprio.shape[0] != n:
         raise ValueError("Non-homogenous batch of (text, image) input -- forward() does not support mixed batches!")
     lo, hi = shard_range(rank, world, n)
-    local = predict(input_ids[lo:hi], pixel_values[lo:hi], proprio[lo:hi])
+    # A rank must reach the collective whatever happens to its shard, or every other rank waits in it forever:
+    # an empty shard (n < world) contributes zero rows instead of calling `predict` with B = 0 (which the engine
+    # rejects), and an exception in `predict` is carried THROUGH the gather - every rank learns that some rank failed
+    # and raises together, after the collective.
+    local, failure = None, None
+    try:
+        if hi > lo:
+            local = predict(input_ids[lo:hi], pixel_values[lo:hi], proprio[lo:hi])
+    except Exception as ex:  # noqa: BLE001 - re-raised below, after the collective
+        failure = ex
+    if world == 1:
+        if failure is not None:
+            raise failure
+        return gather_chunks(local, n, group)
+    bad, shape, dtype, device = _agree_on_chunk_layout(local, failure is not None, group)
+    if failure is not None:
+        raise failure
+    if bad:  # nobody enters the chunk gather: the step is abandoned on every rank
+        raise RuntimeError(f"predict_sharded: rank(s) {bad} failed in their shard; rank {rank} aborts the step with them")
+    if local is None:
+        local = torch.zeros((hi - lo,) + shape, dtype=dtype, device=device)
     return gather_chunks(local, n, group)
+
+
+def _agree_on_chunk_layout(local: Optional[torch.Tensor], failed: bool, group=None):
+    """One small all-gather in front of the chunk gather: every rank announces (failed, has chunk, T, A); ranks without
+    a chunk (empty shard) take the layout of a rank that has one.  Returns (failed ranks, (T, A), dtype, device)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    device = local.device if local is not None else torch.device(
+        "cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor([1 if failed else 0, 0 if local is None else 1,
+                         0 if local is None else local.shape[1], 0 if local is None else local.shape[2]],
+                        dtype=torch.int64, device=device)
+    every = torch.empty(world * 4, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    every = every.cpu().view(world, 4)
+    bad = [r for r in range(world) if every[r, 0]]
+    have = [r for r in range(world) if every[r, 1]]
+    t, a = (int(every[have[0], 2]), int(every[have[0], 3])) if have else (0, 0)
+    return bad, (t, a), (local.dtype if local is not None else torch.float32), device
