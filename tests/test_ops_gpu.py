@@ -33,7 +33,7 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 224, 256])
 def test_gemm_plain(M, N, K, bn):
     from vla_adapter_b200 import ops
 
@@ -47,17 +47,18 @@ def test_gemm_plain(M, N, K, bn):
     assert (out.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-3
 
 
-@pytest.mark.parametrize("act", ["none", "gelu", "relu"])
-def test_gemm_epilogue(act):
+@pytest.mark.parametrize("act,N,bn", [("none", 1152, 0), ("gelu", 1152, 0), ("relu", 1152, 0), ("none", 896, 224),
+                                      ("gelu", 896, 224), ("relu", 1000, 224)])
+def test_gemm_epilogue(act, N, bn):
     from vla_adapter_b200 import ops
 
-    M, N, K = 700, 1152, 896
+    M, K = 700, 896
     a = _randn(M, K, seed=3)
     w = _randn(N, K, scale=K ** -0.5, seed=4)
     bias = torch.randn(N, device="cuda")
     ls = torch.rand(N, device="cuda") + 0.5
     resid = _randn(M, N, seed=5)
-    out = ops.linear(a, w, bias=bias, act=act, colscale=ls, resid=resid)
+    out = ops.linear(a, w, bias=bias, act=act, colscale=ls, resid=resid, force_bn=bn)
     v = a.float() @ w.float().T + bias
     if act == "gelu":
         v = torch.nn.functional.gelu(v)
@@ -67,7 +68,7 @@ def test_gemm_epilogue(act):
     assert _rel(out, ref) < 5e-3
     # in-place residual (C aliases resid)
     x = resid.clone()
-    ops.linear(a, w, bias=bias, act=act, colscale=ls, resid=x, out=x)
+    ops.linear(a, w, bias=bias, act=act, colscale=ls, resid=x, out=x, force_bn=bn)
     # in place the epilogue rounds to bf16 and then TMA-reduce-adds into C (two roundings, like the reference's bf16
     # `x + y`); out of place it adds the residual in fp32 before the single rounding: equal up to one bf16 ulp
     assert _rel(x, ref) < 5e-3

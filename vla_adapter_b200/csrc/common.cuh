@@ -185,10 +185,14 @@ VLA_DEVINL void wd_note(uint32_t slot_addr, uint32_t note) {
 template <class BarOf>
 VLA_DEVINL void wd_monitor(uint32_t done_bar, uint32_t slots_addr, int n_warps, uint32_t kernel, BarOf bar_of) {
   uint32_t polls = 0, t0 = 0;
-  while (!mbar_try_wait(done_bar, 0)) {
+  for (;;) {
+    // Lane 0's poll decides for the whole warp: the loop exit must be warp-uniform, because the code behind it
+    // (__syncthreads, cluster barriers) is .aligned - with per-lane exits the first GEMM launch hung on B200.
+    const bool done = __shfl_sync(0xffffffffu, mbar_try_wait(done_bar, 0) ? 1 : 0, 0) != 0;
+    if (done) break;
     __nanosleep(200);
     if ((++polls & 0x3fffu) != 0) continue;
-    const uint32_t now = static_cast<uint32_t>(global_timer_ns() >> 20) | 1u;
+    const uint32_t now = __shfl_sync(0xffffffffu, static_cast<uint32_t>(global_timer_ns() >> 20) | 1u, 0);
     if (!t0) {
       t0 = now;
       continue;
@@ -220,6 +224,7 @@ VLA_DEVINL void wd_monitor(uint32_t done_bar, uint32_t slots_addr, int n_warps, 
     while (global_timer_ns() - t1 < 100000000ull) __nanosleep(1000);
     __trap();
   }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- TMA

@@ -33,7 +33,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+#ifdef VLA_NO_WATCHDOG  // bisecting aid: the kernel without its monitor warp
+constexpr int GEMM_THREADS = 320;
+#else
 constexpr int GEMM_THREADS = 352;          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue, warp 10 watchdog monitor
+#endif
 constexpr int GEMM_WORK_WARPS = 10;
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB per stage
@@ -47,7 +51,7 @@ struct GemmDev {
   int rows, batches, N, K;
   int mt_per_batch, tiles_m, tiles_n;
   int pack;        // > 0: short row views (rows < 128, 128 % rows == 0): one M tile = `pack` consecutive batches
-  int bn;          // tile width: 64 / 128 / 192 / 256
+  int bn;          // tile width: 64 / 128 / 192 / 224 / 256
   int stages;      // smem ring depth = min(8, 192 KB / stage bytes)
   const float* bias;
   const float* colscale;
@@ -96,6 +100,20 @@ VLA_DEVINL void store_box(const CUtensorMap* mapC, uint32_t buf_addr, int lane, 
     else tma_store_3d(mapC, buf_addr, c0, r0, b);
     tma_store_commit();
   }
+}
+
+// The watchdog monitor of a GEMM CTA (common.cuh), deliberately NOT inlined and fed plain values only: with the record
+// dump inlined into the kernel body (a lambda capturing the barrier-address lambdas by reference) the kernel hung on
+// its first launch on B200 - even in builds whose monitor branch never executed - while this form and a dump-less
+// inline loop both run (bisected on the GPU, round 2).
+__device__ __noinline__ void gemm_monitor(uint32_t done_bar, uint32_t note_base, uint32_t bar_base, uint32_t kernel) {
+  wd_monitor(done_bar, note_base, GEMM_WORK_WARPS, kernel, [bar_base](uint32_t kind, uint32_t idx) {
+    return kind == 1   ? bar_base + 8u * (MAX_STAGES + idx)          // empty(stage)
+           : kind == 2 ? bar_base + 8u * idx                         // full(stage)
+           : kind == 3 ? bar_base + 8u * (2 * MAX_STAGES + 2 + idx)  // tmem_empty(acc)
+           : kind == 4 ? bar_base + 8u * (2 * MAX_STAGES + idx)      // tmem_full(acc)
+                       : 0u;
+  });
 }
 
 // CG = 1: one CTA per 128 x bn output tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x bn tile -
@@ -258,9 +276,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       p.prof[0] = global_timer_ns();
       p.prof[1] = static_cast<unsigned long long>(clock64());
     }
-    wd_monitor(done_bar, note_base, GEMM_WORK_WARPS, CG == 2 ? WD_K_GEMM2 : WD_K_GEMM1, [&](uint32_t kind, uint32_t idx) {
-      return kind == 1 ? empty_bar(idx) : kind == 2 ? full_bar(idx) : kind == 3 ? tempty_bar(idx) : kind == 4 ? tfull_bar(idx) : 0u;
-    });
+    gemm_monitor(done_bar, note_base, bar_base, CG == 2 ? WD_K_GEMM2 : WD_K_GEMM1);
     if (prof) {
       p.prof[2] = global_timer_ns();
       p.prof[3] = static_cast<unsigned long long>(clock64());
@@ -270,7 +286,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     const int e = warp_idx - 2;
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
     const int half = e >> 2;           // which half of the tile's columns
-    const int wcols = p.bn >> 1;       // accumulator columns per warp (multiple of 32)
+    // accumulator columns per warp, in whole 32-column chunks: bn / 2 each, except tile width 224 = 128 + 96
+    const int w0 = ((p.bn >> 1) + 31) & ~31;
+    const int wcols = half ? p.bn - w0 : w0;
+    const int wcol0 = half ? w0 : 0;
     const uint32_t buf0 = staging_base + static_cast<uint32_t>(e) * 4096u;
     int buf = 0;
     int acc = 0;
@@ -288,7 +307,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
         r0 = t0 % p.rows;
       }
       const bool live = p.pack ? b < p.batches : r0 < p.rows;
-      const int n0 = n_idx * p.bn + half * wcols;
+      const int n0 = n_idx * p.bn + wcol0;
       float2 rst = make_float2(1.f, 0.f);  // this thread's row: (rstd, -mean * rstd)
       if (p.row_stats && r0 + lane < p.rows) rst = __ldg(p.row_stats + r0 + lane);
 
@@ -296,7 +315,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(acc * 256 + half * wcols);
+                             static_cast<uint32_t>(acc * 256 + wcol0);
       if (live && n0 < p.N) {  // warp-uniform: sub-tiles entirely out of bounds are skipped
         if (swiglu) {
 #pragma unroll 1
@@ -689,10 +708,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   const int sms = num_sms() / cg;  // scheduling units: CTAs or CTA pairs
   // Tile-width heuristic: fewest (rounds over the SMs) x (tile width + fixed per-tile cost).
   int bn = a.force_bn;
-  if (bn != 64 && bn != 128 && bn != 192 && bn != 256) {
+  if (bn != 64 && bn != 128 && bn != 192 && bn != 224 && bn != 256) {
     long long best = -1;
-    const int cands[4] = {256, 192, 128, 64};
-    for (int i = 0; i < 4; ++i) {
+    // 224 = 896 / 4: Qwen's hidden size (o / down projections, projector fc2 / fc3, every policy projection) tiles
+    // without the 7 % (5 x 192) or 12.5 % (4 x 256) of padded columns
+    const int cands[5] = {256, 224, 192, 128, 64};
+    for (int i = 0; i < 5; ++i) {
       const int c = cands[i];
       if (swiglu && (c & 127)) continue;  // a SwiGLU output box needs 64 accumulator columns per warp
       const long long tiles = static_cast<long long>(tiles_m) * ((a.N + c - 1) / c);

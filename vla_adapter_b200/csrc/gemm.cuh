@@ -37,7 +37,7 @@ struct GemmArgs {
   long long r_batch_stride = 0;
   int ldr = 0;
   int act = ACT_NONE;
-  int force_bn = 0;  // 0 = heuristic, else 64/128/256
+  int force_bn = 0;  // 0 = heuristic, else 64 / 128 / 192 / 224 / 256
   // HF rotate_half RoPE fused into the epilogue (Qwen2 q/k projection): output columns [0, rope_cols) are heads of
   // width 64 rotated with the cos/sin of position (row % rope_S).  rope_cs is the table TRANSPOSED and packed,
   // [32][rope_S] words of (bf16 cos | bf16 sin << 16) (rope_pack_launch): the 32 lanes of an epilogue warp are 32
