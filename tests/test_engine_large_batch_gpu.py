@@ -185,18 +185,22 @@ def test_mixed_prompt_lengths_in_one_batch(pro, B):
     # list-of-rows form of the same call
     _, n_list = eng.predict_action_batch([ids[b, :lens[b]] for b in range(B)], None, pix, prop)
     assert np.array_equal(n_list, normalized)
-    worst_alone, worst_oracle = 0.0, 0.0
+    worst_alone, worst_oracle, worst_ref = 0.0, 0.0, 0.0
     for b in range(B):
         i1 = ids[b:b + 1, :lens[b]]
         _, n1, h1 = eng.predict_action_batch(i1, None, pix[b:b + 1], prop[b:b + 1], return_hidden=True)
         worst_alone = max(worst_alone, float(np.abs(n1[0] - normalized[b]).max()))
         assert torch.equal(h1[0], ha[b]), f"sample {b}: last-layer ActionQuery states differ from the stand-alone run"
-        t = O.predict_action_batch(W, cfg, pix[b:b + 1], i1, prop[b:b + 1], torch.float32)["normalized"].numpy()
-        worst_oracle = max(worst_oracle, float(np.abs(t[0] - normalized[b]).max()))
+        if b < 5:   # the oracle (fp32 truth and the reference-precision bf16 run) on its own un-padded prompt
+            t = O.predict_action_batch(W, cfg, pix[b:b + 1], i1, prop[b:b + 1], torch.float32)["normalized"].numpy()
+            r = O.predict_action_batch(W, cfg, pix[b:b + 1], i1, prop[b:b + 1], torch.bfloat16)["normalized"].numpy()
+            worst_oracle = max(worst_oracle, float(np.abs(t[0] - normalized[b]).max()))
+            worst_ref = max(worst_ref, float(np.abs(t[0] - r[0]).max()))
     eng.close()
-    print(f"pro={pro} B={B}: max |batched - alone| = {worst_alone:.2e}, max |batched - fp32 oracle| = {worst_oracle:.4f}")
+    print(f"pro={pro} B={B}: max |batched - alone| = {worst_alone:.2e}, max |batched - fp32 oracle| = {worst_oracle:.4f} "
+          f"(bf16 oracle {worst_ref:.4f})")
     assert worst_alone <= 2e-3       # same arithmetic per row; only the batch-size branch (B = 1 vs B) may differ
-    assert worst_oracle <= 3e-2
+    assert worst_oracle <= max(2 * worst_ref, 2e-2)
     with pytest.raises(ValueError):  # a zero-length prompt
         eng2 = _engine(cfg, W, 2, 4)
         try:
