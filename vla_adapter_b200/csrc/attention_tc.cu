@@ -180,7 +180,7 @@ template <int HD, int NLIVE, bool MASKED, bool SPLIT>
 VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint32_t tO, int k0h, int grow, int j, int half,
                                 float sl2, float& m_ref, float& l, float* xch_mine, const float* xch_other, int bar_id,
                                 uint32_t turn_wait, uint32_t turn_parity, uint32_t turn_arrive, uint32_t s_free_bar,
-                                uint32_t pv_done_bar, uint32_t pv_parity, uint32_t my_note) {
+                                uint32_t pv_done_bar, uint32_t pv_parity) {
   uint32_t v[NLIVE > 0 ? NLIVE : 1][32];
   float mloc = -INFINITY;
   if (NLIVE > 0) {
@@ -230,7 +230,6 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
     m_new = fmaxf(m_new, *xch_other);
   }
   if (pv_done_bar) {  // PV of the previous tile has retired: O is stable and the P columns may be rewritten
-    wd_note(my_note, VLA_WD_NOTE(9, 0, pv_parity, j));
     mbar_wait(pv_done_bar, pv_parity);
     tc_fence_after();
   }
@@ -260,7 +259,6 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
   // The exponentials of the two slots take turns: while one slot owns the MUFU, the other's P -> PV -> next QK ->
   // TMEM load -> row max chain runs on the tensor pipe, instead of both slots doing each phase in lockstep.
   if (turn_wait) {
-    wd_note(my_note, VLA_WD_NOTE(10, 0, turn_parity, j));
     mbar_wait(turn_wait, turn_parity);
   }
   if (NLIVE > 0) {
@@ -374,17 +372,14 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   auto kv_full = [&](int s) { return bar_base + 8u * (22 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (22 + NS + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_BAR + 8 * (22 + 2 * NS));
-  // watchdog (common.cuh): warp 3 is the monitor, parked on done_bar; every other warp arrives there at its end and
-  // leaves a note (which barrier, parity, step) before each wait
+  // watchdog (common.cuh): warp 3 is the monitor, parked on done_bar; every other warp arrives there at its end
   constexpr int N_WARPS = L::THREADS / 32;
   const uint32_t done_bar = bar_base + 8u * (23 + 2 * NS);
-  const uint32_t note_base = bar_base + 8u * (24 + 2 * NS);
 
   // shfl-broadcast warp index: the role branches are then provably warp-uniform, so the MMA warp's descriptor
   // arithmetic stays on the uniform datapath and tcgen05.mma issues at the hardware rate (scripts/ubench/mma3.cu)
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t my_note = note_base + 4u * static_cast<uint32_t>(warp_idx);
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&mapQ);
@@ -436,7 +431,6 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       for (int x = 0; x < 2; ++x) {
         if (!it.n[x]) continue;
         const int qb = x * 2 + static_cast<int>(q_cnt[x] & 1u);
-        wd_note(my_note, VLA_WD_NOTE(1, qb, ((q_cnt[x] >> 1) & 1u) ^ 1u, item));
         mbar_wait_relaxed(q_empty(qb), ((q_cnt[x] >> 1) & 1u) ^ 1u);
         ++q_cnt[x];
         if (elect_one()) {
@@ -451,7 +445,6 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const int s = static_cast<int>(kv_cnt % NS);
         const uint32_t ph = (kv_cnt / NS) & 1u;
         ++kv_cnt;
-        wd_note(my_note, VLA_WD_NOTE(2, s, ph ^ 1u, kv_cnt));
         mbar_wait_relaxed(kv_empty(s), ph ^ 1u);
         if (elect_one()) {
           fa_trace(p, 0, tr_cnt, 100 + j);
@@ -488,7 +481,6 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       auto need_kv = [&](int j) {
         while (kv_waited <= j) {
           const uint32_t c = kv0 + kv_waited;
-          wd_note(my_note, VLA_WD_NOTE(3, c % NS, (c / NS) & 1u, c));
           mbar_wait(kv_full(static_cast<int>(c % NS)), (c / NS) & 1u);
           ++kv_waited;
         }
@@ -543,7 +535,6 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       };
       if (n_x) {
         qbuf = x * 2 + static_cast<int>(q_cnt & 1u);
-        wd_note(my_note, VLA_WD_NOTE(4, qbuf, (q_cnt >> 1) & 1u, item));
         mbar_wait(q_full(qbuf), (q_cnt >> 1) & 1u);
         ++q_cnt;
         tc_fence_after();
@@ -553,18 +544,15 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         if (j < n_x) {
           if (L::DEALIAS) {
             // the next tile's scores as soon as this tile's have been read: S(j+1) is ready before softmax(j) ends
-            wd_note(my_note, VLA_WD_NOTE(5, x, f_cnt & 1u, f_cnt));
             mbar_wait(s_free(x), f_cnt & 1u);
             ++f_cnt;
             tc_fence_after();
             if (j + 1 < n_x && !(p.debug & 16)) issue_qk(j + 1);
           }
-          wd_note(my_note, VLA_WD_NOTE(6, x, p_cnt & 1u, p_cnt));
           mbar_wait(p_ready(x), p_cnt & 1u);
           if (lane == 0) fa_trace(p, 1, tr_cnt, 300 + x * 10 + j);
           ++p_cnt;
           if (j == 0) {  // previous item's epilogue has drained O_x
-            wd_note(my_note, VLA_WD_NOTE(7, x, (o_cnt & 1u) ^ 1u, o_cnt));
             mbar_wait(o_empty(x), (o_cnt & 1u) ^ 1u);
           }
           tc_fence_after();
@@ -595,21 +583,12 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       }
     }
   } else if (warp_idx == 3) {
+#ifndef VLA_NO_WATCHDOG
     // ------------------------------------------------------------ watchdog monitor (see common.cuh)
-    wd_monitor(done_bar, note_base, N_WARPS, HD == 64 ? WD_K_FA64 : WD_K_FA72, [&](uint32_t kind, uint32_t idx) {
-      switch (kind) {
-        case 1: return q_empty(idx);
-        case 2: return kv_empty(idx);
-        case 3: return kv_full(idx);
-        case 4: return q_full(idx);
-        case 5: return s_free(idx);
-        case 6: return p_ready(idx);
-        case 7: return o_empty(idx);
-        case 8: return s_full(idx);
-        case 11: return o_full(idx);
-        default: return 0u;  // pv_done / turn notes carry no slot index: the slot follows from the warp number
-      }
-    });
+    // minimal form: this warp lives in the 32-register warpgroup, and a barrier dump inlined here made ptxas spill
+    // inside the MMA-issuing warps' loops (230 us instead of 134 us per DINOv2 layer)
+    wd_monitor_min(done_bar, HD == 64 ? WD_K_FA64 : WD_K_FA72);
+#endif
   }
   } else {
     if (L::SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
@@ -649,7 +628,6 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         int nvalid = p.Skv - k0;
         if (nvalid > BN) nvalid = BN;
         const int nch = (nvalid + 31) >> 5;           // 32-key chunks holding valid keys
-        wd_note(my_note, VLA_WD_NOTE(8, x, s_cnt & 1u, s_cnt));
         mbar_wait(s_full(x), s_cnt & 1u);
         ++s_cnt;
         tc_fence_after();
@@ -681,13 +659,13 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           const uint32_t d_bar = (L::DEALIAS && j > 0) ? pv_done(x) : 0u, d_par = d_cnt & 1u;
           if (L::DEALIAS && j > 0) ++d_cnt;
           if (my_live == 2) {
-            if (masked) fa_softmax_tile<HD, 2, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
-            else fa_softmax_tile<HD, 2, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
+            if (masked) fa_softmax_tile<HD, 2, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            else fa_softmax_tile<HD, 2, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           } else if (my_live == 1) {
-            if (masked) fa_softmax_tile<HD, 1, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
-            else fa_softmax_tile<HD, 1, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
+            if (masked) fa_softmax_tile<HD, 1, true, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
+            else fa_softmax_tile<HD, 1, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           } else {
-            fa_softmax_tile<HD, 0, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par, my_note);
+            fa_softmax_tile<HD, 0, false, L::SPLIT>(p, tSh, tPh, tO, k0h, grow, j, half, sl2, m_ref, l, xm, xo, bar_id, t_wait, t_par, t_arr, f_bar, d_bar, d_par);
           }
           if (my_live < my_all) {  // causal chunks above the diagonal: P = 0
             uint32_t z[16];
@@ -703,7 +681,6 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           // pins the order.
           mbar_arrive(s_free(x));
           if (j > 0) {
-            wd_note(my_note, VLA_WD_NOTE(9, x, d_cnt & 1u, d_cnt));
             mbar_wait(pv_done(x), d_cnt & 1u);
             ++d_cnt;
           }
@@ -722,7 +699,6 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         named_bar_sync(bar_id, 64);
         l_tot = l + *xo;
       }
-      wd_note(my_note, VLA_WD_NOTE(11, x, o_cnt & 1u, o_cnt));
       mbar_wait_relaxed(o_full(x), o_cnt & 1u);
       ++o_cnt;
       tc_fence_after();
@@ -795,10 +771,9 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
   }
 
   if (L::TMA_EPI && warp_idx >= 4 && lane == 0) tma_store_wait<0>();  // output stores have left shared memory
-  if (warp_idx != 3) {  // this warp's role is complete
-    wd_note(my_note, 0xffffffffu);
-    if (lane == 0) mbar_arrive(done_bar);
-  }
+#ifndef VLA_NO_WATCHDOG
+  if (warp_idx != 3 && lane == 0) mbar_arrive(done_bar);  // this warp's role is complete
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp_idx == 1) {

@@ -145,7 +145,7 @@ VLA_DEVINL void mbar_wait_short(uint32_t bar, uint32_t parity) {
 struct WdRecord {
   uint32_t magic, kernel, block, smid, warp, note, bar_lo, bar_hi;
 };
-constexpr unsigned int WD_MAX_RECORDS = 63;
+constexpr unsigned int WD_MAX_RECORDS = 127;
 struct WdBuf {
   unsigned int pad[8];
   WdRecord rec[WD_MAX_RECORDS];
@@ -177,52 +177,96 @@ VLA_DEVINL unsigned long long global_timer_ns() {
   return t;
 }
 // Working warps: "I am about to wait on this barrier" (all lanes store the same word: one instruction, no branch).
+// -DVLA_NO_WATCHDOG compiles the whole mechanism out (A/B measurements of its cost).
 VLA_DEVINL void wd_note(uint32_t slot_addr, uint32_t note) {
+#ifndef VLA_NO_WATCHDOG
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot_addr), "r"(note) : "memory");
+#endif
 }
-// Monitor warp (all 32 lanes): returns when `done_bar` completes; on timeout dumps `n_warps` notes (slots_addr[w]) and
-// the barrier each note names (bar_of(kind, idx) -> shared address or 0), then traps.
+// Cold end of wd_monitor_min: ONE 16-byte store {magic, kernel, CTA, 0xffffffff} at a slot derived from the CTA index,
+// a system fence, the trap.  It has to stay this small: struct stores through a generic pointer, an atomic slot counter
+// or a grace loop here made ptxas spill throughout the attention kernel's 32-register warpgroup (12 -> 380 bytes).
+VLA_DEVINL void wd_record_min(uint32_t kernel) {
+  WdBuf* w = g_wd_buf;
+  if (w) {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\tfence.acq_rel.sys;"
+                 ::"l"(&w->rec[blockIdx.x % WD_MAX_RECORDS]), "r"(WD_MAGIC), "r"(kernel), "r"(blockIdx.x), "r"(0xffffffffu)
+                 : "memory");
+  }
+  __trap();
+}
+
+// Monitor warp (all 32 lanes enter; lane 0 does the waiting): returns when `done_bar` completes.  On timeout lane 0
+// dumps `n_warps` notes (slots_addr[w]) with the barrier each note names (bar_of(kind, idx) -> shared address or 0),
+// then the raw words of the `n_bars` mbarriers starting at `bars_addr` (records with warp = 0x100 + index), and traps.
+// The wait is a bare try_wait loop: the hardware suspends the lane until the barrier completes or its own time limit
+// expires, so the warp costs no issue slots and wakes at once - with a 200 ns back-off per poll the monitor's wake-up
+// latency at the end of every kernel added 0.5 ms to the 800-kernel bs=1 forward.  The exit is warp-uniform
+// (__syncwarp), as the .aligned barriers behind it require.
 template <class BarOf>
-VLA_DEVINL void wd_monitor(uint32_t done_bar, uint32_t slots_addr, int n_warps, uint32_t kernel, BarOf bar_of) {
-  uint32_t polls = 0, t0 = 0;
-  for (;;) {
-    // Lane 0's poll decides for the whole warp: the loop exit must be warp-uniform, because the code behind it
-    // (__syncthreads, cluster barriers) is .aligned - with per-lane exits the first GEMM launch hung on B200.
-    const bool done = __shfl_sync(0xffffffffu, mbar_try_wait(done_bar, 0) ? 1 : 0, 0) != 0;
-    if (done) break;
-    __nanosleep(200);
-    if ((++polls & 0x3fffu) != 0) continue;
-    const uint32_t now = __shfl_sync(0xffffffffu, static_cast<uint32_t>(global_timer_ns() >> 20) | 1u, 0);
-    if (!t0) {
-      t0 = now;
-      continue;
-    }
-    if (now - t0 <= g_wd_limit_ticks) continue;
-    WdBuf* w = g_wd_buf;
-    if (w) {
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      for (int wi = static_cast<int>(threadIdx.x & 31u); wi < n_warps; wi += 32) {
-        uint32_t note;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(note) : "r"(slots_addr + 4u * wi));
-        const uint32_t bar = bar_of(note >> 24, (note >> 16) & 0xffu);
-        uint32_t lo = 0, hi = 0;
-        if (bar) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(bar));
-        const unsigned int slot = atomicAdd(&g_wd_slots, 1u);
-        if (slot < WD_MAX_RECORDS) {
-          volatile WdRecord* r = &w->rec[slot];
-          r->kernel = kernel; r->block = blockIdx.x; r->smid = smid; r->warp = static_cast<uint32_t>(wi);
-          r->note = note; r->bar_lo = lo; r->bar_hi = hi;
-          __threadfence_system();
-          r->magic = WD_MAGIC;
-        }
+VLA_DEVINL void wd_monitor(uint32_t done_bar, uint32_t slots_addr, int n_warps, uint32_t kernel, BarOf bar_of,
+                           uint32_t bars_addr = 0, int n_bars = 0) {
+  if ((threadIdx.x & 31u) == 0) {
+    uint32_t polls = 0, t0 = 0;
+    while (!mbar_try_wait(done_bar, 0)) {
+      if ((++polls & 0xffu) != 0) continue;
+      const uint32_t now = static_cast<uint32_t>(global_timer_ns() >> 20) | 1u;
+      if (!t0) {
+        t0 = now;
+        continue;
       }
-      __threadfence_system();
+      if (now - t0 <= g_wd_limit_ticks) continue;
+      WdBuf* w = g_wd_buf;
+      if (w) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        for (int i = 0; i < n_warps + n_bars; ++i) {
+          uint32_t note = 0, lo = 0, hi = 0, who;
+          if (i < n_warps) {
+            who = static_cast<uint32_t>(i);
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(note) : "r"(slots_addr + 4u * i));
+            const uint32_t bar = bar_of(note >> 24, (note >> 16) & 0xffu);
+            if (bar) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(bar));
+          } else {
+            who = 0x100u + static_cast<uint32_t>(i - n_warps);
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(bars_addr + 8u * (i - n_warps)));
+          }
+          const unsigned int slot = atomicAdd(&g_wd_slots, 1u);
+          if (slot < WD_MAX_RECORDS) {
+            volatile WdRecord* r = &w->rec[slot];
+            r->kernel = kernel; r->block = blockIdx.x; r->smid = smid; r->warp = who;
+            r->note = note; r->bar_lo = lo; r->bar_hi = hi;
+            __threadfence_system();
+            r->magic = WD_MAGIC;
+          }
+        }
+        __threadfence_system();
+      }
+      // grace period: monitors of other stuck CTAs get to write their records before the trap takes the context down
+      const unsigned long long t1 = global_timer_ns();
+      while (global_timer_ns() - t1 < 100000000ull) __nanosleep(1000);
+      __trap();
     }
-    // grace period: monitors of other stuck CTAs get to write their records before the trap takes the context down
-    const unsigned long long t1 = global_timer_ns();
-    while (global_timer_ns() - t1 < 100000000ull) __nanosleep(1000);
-    __trap();
+  }
+  __syncwarp();
+}
+
+// The same monitor without the barrier dump, for warps that have no registers to spare (the attention kernel's
+// monitor lives in the 32-register warpgroup: with the full dump inlined there ptxas spilled inside the MMA-issuing
+// warps' loops and the kernel ran 230 us instead of 134 us).  The record carries the kernel, CTA and SM only.
+VLA_DEVINL void wd_monitor_min(uint32_t done_bar, uint32_t kernel) {
+  if ((threadIdx.x & 31u) == 0) {
+    uint32_t polls = 0, t0 = 0;
+    while (!mbar_try_wait(done_bar, 0)) {
+      if ((++polls & 0xffu) != 0) continue;
+      const uint32_t now = static_cast<uint32_t>(global_timer_ns() >> 20) | 1u;
+      if (!t0) {
+        t0 = now;
+        continue;
+      }
+      if (now - t0 <= g_wd_limit_ticks) continue;
+      wd_record_min(kernel);
+    }
   }
   __syncwarp();
 }

@@ -479,10 +479,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     }
     if (lane == 0) tma_store_wait_read<0>();  // staging smem must outlive the last bulk reads
   }
+#ifndef VLA_NO_WATCHDOG
   if (warp_idx < GEMM_WORK_WARPS) {  // this warp's role is complete
     wd_note(my_note, 0xffffffffu);
     if (lane == 0) mbar_arrive(done_bar);
   }
+#endif
 
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // neither CTA may leave while the pair's MMAs / remote arrivals can touch it

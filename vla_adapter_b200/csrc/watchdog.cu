@@ -127,7 +127,21 @@ std::string watchdog_report() {
     if (r.magic != WD_MAGIC) continue;
     const uint32_t k = r.kernel, note = r.note;
     char line[320];
-    if (note == 0xffffffffu) {
+    if (r.smid == 0xffffffffu) {  // minimal record (wd_monitor_min)
+      snprintf(line, sizeof(line), "watchdog: %s CTA %u did not finish within the time limit\n", kernel_name(k), r.block);
+    } else if (r.warp >= 0x100u) {
+      static const char* fa_bars[] = {"q_full[0]", "q_full[1]", "q_full[2]", "q_full[3]", "q_empty[0]", "q_empty[1]",
+                                      "q_empty[2]", "q_empty[3]", "s_full[A]", "s_full[B]", "p_ready[A]", "p_ready[B]",
+                                      "o_full[A]", "o_full[B]", "o_empty[A]", "o_empty[B]", "turn[A]", "turn[B]",
+                                      "s_free[A]", "s_free[B]", "pv_done[A]", "pv_done[B]"};
+      const uint32_t i = r.warp - 0x100u;
+      char name[32];
+      if ((k == WD_K_FA64 || k == WD_K_FA72) && i < 22) snprintf(name, sizeof(name), "%s", fa_bars[i]);
+      else if (k == WD_K_FA64 || k == WD_K_FA72) snprintf(name, sizeof(name), "kv ring barrier %u", i - 22);
+      else snprintf(name, sizeof(name), "barrier %u", i);
+      snprintf(line, sizeof(line), "watchdog: %s CTA %u (SM %u): %s word 0x%08x%08x\n", kernel_name(k), r.block, r.smid, name,
+               r.bar_hi, r.bar_lo);
+    } else if (note == 0xffffffffu) {
       snprintf(line, sizeof(line), "watchdog: %s CTA %u (SM %u) warp %u (%s): finished its role\n", kernel_name(k), r.block,
                r.smid, r.warp, role_name(k, r.warp));
     } else if (note == 0) {
