@@ -68,6 +68,23 @@ struct FaDev {
   uint32_t items[FA_MAX_ITEMS];
 };
 
+// The timing-experiment switches (FaDev::debug) and the event trace exist in the trace build only
+// (-DVLA_FA_TRACE_BUILD); in the product build every switch is a compile-time zero and its branch disappears.
+#ifdef VLA_FA_TRACE_BUILD
+#define FA_DBG(p, mask) ((p).debug & (mask))
+#else
+#define FA_DBG(p, mask) 0
+#endif
+// Exp-phase turn taking between the two slots (A(j) -> B(j) -> A(j+1) ...: one slot owns the MUFU while the other's
+// P -> PV -> next QK chain runs) is OFF: measured on B200 at bs=64 it is worth +4 % on the DINOv2 shape, +5 % on SigLIP
+// and -1.5 % on Qwen - 9.30 ms against 9.24 ms of attention per step, nothing - and its original form was the source of
+// an intermittent deadlock (see do_turn below).  -DVLA_FA_TURNS=1 brings the (repaired) protocol back.
+#if defined(VLA_FA_TURNS) && VLA_FA_TURNS
+constexpr bool FA_TURNS = true;
+#else
+constexpr bool FA_TURNS = false;
+#endif
+
 struct FaItem {
   int b, g;
   int h[2], qb[2], n[2];  // per slot: absolute query head, query tile, number of key tiles (0 = idle)
@@ -184,7 +201,7 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
   uint32_t v[NLIVE > 0 ? NLIVE : 1][32];
   float mloc = -INFINITY;
   if (NLIVE > 0) {
-    if (p.debug & 64) {  // timing experiment: no TMEM loads
+    if (FA_DBG(p, 64)) {  // timing experiment: no TMEM loads
 #pragma unroll
       for (int c = 0; c < NLIVE; ++c)
 #pragma unroll
@@ -224,7 +241,7 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
   }
   // row max over the whole tile: one float per row each way, one 64-thread named barrier
   float m_new = fmaxf(m_ref, mloc);
-  if (SPLIT && !(p.debug & 256)) {
+  if (SPLIT && !(FA_DBG(p, 256))) {
     *xch_mine = mloc;
     named_bar_sync(bar_id, 64);
     m_new = fmaxf(m_new, *xch_other);
@@ -271,7 +288,7 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2v, nmb);
-        if (p.debug & 32) {  // timing experiment: no MUFU work
+        if (FA_DBG(p, 32)) {  // timing experiment: no MUFU work
           v[c][2 * i] = __float_as_uint(t.x);
           v[c][2 * i + 1] = __float_as_uint(t.y);
         } else {
@@ -287,7 +304,7 @@ VLA_DEVINL void fa_softmax_tile(const FaDev& p, uint32_t tSh, uint32_t tPh, uint
         sum2 = __fadd2_rn(sum2, e);
         pk[i] = pack_bf16(e.x, e.y);
       }
-      if (!(p.debug & 128)) tmem_st_32x32b_x16(tPh + c * 16, pk);
+      if (!(FA_DBG(p, 128))) tmem_st_32x32b_x16(tPh + c * 16, pk);
     }
     l += sum2.x + sum2.y;
   }
@@ -499,7 +516,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const uint32_t idesc_qk = make_idesc_bf16(128, static_cast<uint32_t>(n16_of(j) * 16));
         const uint32_t sq = sbase + L::OFF_Q + qbuf * FA_TILE_BYTES, sk = sbase + L::OFF_K + s * L::KV_TILE;
         if (elect_one()) {
-          if (!(p.debug & 4)) {
+          if (!(FA_DBG(p, 4))) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tS, make_smem_desc(sq + k * 32, 1024, LAYOUT_SW128),
@@ -519,7 +536,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const int n16 = n16_of(j);
         const uint32_t sv = sbase + L::OFF_V + s * L::KV_TILE;
         if (elect_one()) {
-          if (!(p.debug & 2)) {
+          if (!(FA_DBG(p, 2))) {
             for (int kk = 0; kk < n16; ++kk)
               umma_bf16_ts(tO, tP + kk * 8, make_smem_desc(sv + kk * 2048, 1024, LAYOUT_SW128), idesc_pv,
                            (j | kk) != 0 ? 1u : 0u);
@@ -547,7 +564,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             mbar_wait(s_free(x), f_cnt & 1u);
             ++f_cnt;
             tc_fence_after();
-            if (j + 1 < n_x && !(p.debug & 16)) issue_qk(j + 1);
+            if (j + 1 < n_x && !(FA_DBG(p, 16))) issue_qk(j + 1);
           }
           mbar_wait(p_ready(x), p_cnt & 1u);
           if (lane == 0) fa_trace(p, 1, tr_cnt, 300 + x * 10 + j);
@@ -561,7 +578,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             if (L::DEALIAS) {
               if (elect_one()) umma_commit(pv_done(x));  // P_x / O_x may be touched again by the softmax warps
               __syncwarp();
-              if (p.debug & 16) issue_qk(j + 1);  // (experiment: no early issue)
+              if (FA_DBG(p, 16)) issue_qk(j + 1);  // (experiment: no early issue)
             } else {
               issue_qk(j + 1);  // in-order after PV(j): S_x / P_x is free again
             }
@@ -610,6 +627,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     const float sl2 = p.scale_log2;
     uint32_t s_cnt = 0, o_cnt = 0, x_cnt = 0, t_cnt = 0, d_cnt = 0;
     unsigned int tr_cnt = 0;
+    if (FA_TURNS && x == 1 && lane == 0) mbar_arrive(turn(0));  // slot A's first turn is pre-paid (see do_turn below)
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const FaItem it = fa_decode(p, item);
       const int n_it = it.n[x];
@@ -617,11 +635,11 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       const int q0 = it.qb[x] * FA_BM;
       const int grow = q0 + row;
       const int wrow0 = q0 + quarter * 32;            // first query row of this warp
-      const bool warp_active = wrow0 < p.Sq && !(p.debug & 1);  // all-padding warps only keep the barriers moving
+      const bool warp_active = wrow0 < p.Sq && !(FA_DBG(p, 1));  // all-padding warps only keep the barriers moving
       float m_ref = -INFINITY, l = 0.f;
       // turn taking needs both slots busy with all their warps (padding-only warps would break the arrival counts)
-      const bool pp = !(p.debug & 8) && it.n[0] && it.n[1] && it.qb[0] * FA_BM + FA_BM <= p.Sq &&
-                      it.qb[1] * FA_BM + FA_BM <= p.Sq && !(p.debug & 1);
+      const bool pp = FA_TURNS && !(FA_DBG(p, 8)) && it.n[0] && it.n[1] && it.qb[0] * FA_BM + FA_BM <= p.Sq &&
+                      it.qb[1] * FA_BM + FA_BM <= p.Sq && !(FA_DBG(p, 1));
       const int m_pp = it.n[0] < it.n[1] ? it.n[0] : it.n[1];
       for (int j = 0; j < n_it; ++j) {
         const int k0 = j * BN;
@@ -649,11 +667,16 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
           float* xm = xch + (x_cnt & 1u) * 256 + half * 128 + row;
           const float* xo = xch + (x_cnt & 1u) * 256 + (half ^ 1) * 128 + row;
           ++x_cnt;
-          // exp-phase turn taking while both slots are busy: A(j) -> B(j) -> A(j+1) ...
-          const bool do_wait = pp && (x == 0 ? (j > 0 && j < m_pp) : (j < m_pp));
-          const bool do_arrive = pp && (x == 0 ? (j < m_pp) : (j + 1 < m_pp));
-          const uint32_t t_wait = do_wait ? turn(x) : 0u, t_par = t_cnt & 1u, t_arr = do_arrive ? turn(x ^ 1) : 0u;
-          if (do_wait) ++t_cnt;
+          // exp-phase turn taking while both slots are busy: A(j) -> B(j) -> A(j+1) ...  The protocol is symmetric:
+          // each slot waits for the other's hand-over before EVERY common tile and hands over after it; slot B's
+          // hand-over after the last common tile of an item is the one slot A collects at tile 0 of its next
+          // turn-taking item (the very first one is pre-paid before the item loop).  Before this, A did not wait at
+          // tile 0: it could finish its item and announce tile 0 of the next one while a stalled warp of B had not yet
+          // observed A's previous announcement - the barrier was then two phases ahead of that warp's parity and the
+          // two slots waited for each other forever (an intermittent hang on SM-contended multi-GPU runs).
+          const bool do_turn = pp && j < m_pp;
+          const uint32_t t_wait = do_turn ? turn(x) : 0u, t_par = t_cnt & 1u, t_arr = do_turn ? turn(x ^ 1) : 0u;
+          if (do_turn) ++t_cnt;
           // de-aliased P: announce "scores read" after the TMEM loads, wait for PV(j-1) before touching O / P
           const uint32_t f_bar = L::DEALIAS ? s_free(x) : 0u;
           const uint32_t d_bar = (L::DEALIAS && j > 0) ? pv_done(x) : 0u, d_par = d_cnt & 1u;
@@ -708,7 +731,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       constexpr int GMAX = L::SPLIT ? G - G0 : G;
       uint32_t o[GMAX][8];
       const int g_lo = half ? G0 : 0, g_n = half ? G - G0 : G0;
-      if (warp_active && !(p.debug & 1024)) {
+      if (warp_active && !(FA_DBG(p, 1024))) {
 #pragma unroll
         for (int c = 0; c < GMAX; ++c)
           if (c < g_n) tmem_ld_32x32b_x8(tO + (g_lo + c) * 8, o[c]);
@@ -717,7 +740,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
       tc_fence_before();
       mbar_arrive(o_empty(x));  // O_x may be overwritten by the next item's first PV
       if constexpr (L::TMA_EPI) {
-        if (warp_active && !(p.debug & 512)) {  // rows past Sq are clipped by the TMA unit
+        if (warp_active && !(FA_DBG(p, 512))) {  // rows past Sq are clipped by the TMA unit
           const float inv = 1.0f / l_tot;
           const uint32_t stg = sbase + L::OFF_STG + static_cast<uint32_t>(warp_idx - 4) * 2048u;
           if (lane == 0) tma_store_wait_read<0>();  // the previous item's store has left this buffer
@@ -752,7 +775,7 @@ fa_tcgen05_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             }
           }
         }
-      } else if (warp_active && grow < p.Sq && !(p.debug & 512)) {
+      } else if (warp_active && grow < p.Sq && !(FA_DBG(p, 512))) {
         const float inv = 1.0f / l_tot;
         __nv_bfloat16* dst = p.out + (static_cast<long long>(it.b) * p.q_rows + grow) * p.ld_out + it.h[x] * HD + g_lo * 8;
 #pragma unroll
@@ -909,7 +932,7 @@ int launch_fa(const __nv_bfloat16* q, int ld_q, int Sq, const __nv_bfloat16* k, 
   p.ld_out = ld_out;
   {
     const char* dbg = getenv("VLA_FA_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
+    p.debug = dbg ? atoi(dbg) : 0;  // read by the kernel in the trace build only (FA_DBG)
   }
   const char* trace_path = getenv("VLA_FA_TRACE");
   p.trace = nullptr;
