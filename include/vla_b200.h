@@ -189,6 +189,16 @@ int vla_op_norm_gemm(const void* x, int rows, int ldx, const void* W, int ldw, i
                      const float* bias, const float* colsum, int rms, float eps, int act, float* stats,
                      void* stream);
 
+/* The tail of a transformer block the way the engine chains it, statistics kernel-free (csrc/gemm.cuh stat_out /
+ * stat_in): (1) x[rows, D] += colscale1 * (a @ W1^T + bias1) IN PLACE - the residual box is TMA-loaded into the
+ * epilogue's staging box and added in fp32 - while the epilogue leaves 12 partial (sum, sum of squares) pairs per row in
+ * `partials` ([rows][12][2] fp32); (2) out = act(Linear(Norm(x))) with the norm folded into W2 / bias2 / colsum2
+ * (vla_op_fold_norm) and mean / rstd finished from the partials in the second GEMM's epilogue.  rms != 0: RMSNorm. */
+int vla_op_block_tail(const void* a, int lda, int rows, const void* W1, int ldw1, int K1, void* x, int D,
+                      const float* bias1, const float* colscale1, const void* W2, int ldw2, int N2, void* out, int ldo,
+                      const float* bias2, const float* colsum2, int rms, float eps, int act, float* partials,
+                      void* stream);
+
 /* Multi-head attention over a packed qkv buffer.
  *   q at qkv[row, q_off + h*hd], k at qkv[row, k_off + (h/group)*hd], v likewise; row = b*S + s.
  *   hd in {64, 72}; causal != 0 applies the lower-triangular mask; scale = hd^-0.5. */

@@ -1,14 +1,7 @@
 #!/bin/bash
-# A/B of one environment switch on the same box: scripts/ab_env.sh VAR [rounds]  (bench value with VAR unset / VAR=1)
-VAR=$1; R=${2:-2}
-for i in $(seq $R); do
-  for v in "" 1; do
-    if [ -z "$v" ]; then unset $VAR; else export $VAR=$v; fi
-    timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --latency-iters 0 2>/dev/null | python -c "
-import json,sys,os
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-s=d['segments']
-print('$VAR=%s' % os.environ.get('$VAR',''), round(d['value'],1), round(d['ms_per_step'],2), 'towers', round(s['towers_projector_ms'],2), 'prefill', round(s['llm_prefill_ms'],2), 'policy', round(s['policy_ms'],2), 'gemm_ms', round(d['roofline']['gemm_ms_per_step'],2), d['clocks']['sm_mhz'])
-"
-  done
+# A/B of two environments on the SAME box: scripts/ab_env.sh "ENV_A=.. ENV_B=.." "ENV_C=.." [bench args]  (A B A B)
+A=$1; B=$2; shift 2
+for envs in "$A" "$B" "$A" "$B"; do
+  env $envs python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --latency-iters 100 "$@" 2>/dev/null | \
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); s=d['segments']; print('[$envs]', 'value %.1f ms %.2f gemm %.2f frac %.3f towers %.2f llm %.2f policy %.2f bs1 %.3f launches/step %d' % (d['value'], d['ms_per_step'], d['roofline']['gemm_ms_per_step'], d['roofline']['frac'], s['towers_projector_ms'], s['llm_prefill_ms'], s['policy_ms'], d['latency_bs1']['p50_ms'], d['gpu_launches']/10))"
 done

@@ -334,3 +334,56 @@ def test_rope():
     assert (got.float() - ref.float()).abs().max().item() <= 0.0625     # rare 1-ulp table flips only
     assert (got.float() - ref.float()).abs().mean().item() < 1e-3
     assert torch.equal(y[:, (H + HKV) * hd:], x[:, (H + HKV) * hd:])     # v untouched
+
+
+@pytest.mark.parametrize("rows,K1,D,N2,act,rms,ls", [
+    (1000, 1024, 1024, 4096, "gelu", False, True),    # DINOv2: proj (+LayerScale) -> norm2 -> fc1 + GELU
+    (777, 4304, 1152, 3456, "none", False, False),    # SigLIP: fc2 -> next block's norm1 -> qkv
+    (1250, 896, 896, 9728, "swiglu", True, False),    # Qwen: o-proj -> post_attention RMSNorm -> gate|up + SwiGLU
+    (300, 4864, 896, 1152, "none", True, False),      # Qwen: down-proj -> next layer's input RMSNorm -> q|k|v
+])
+def test_block_tail_statistics_from_the_producing_gemm(rows, K1, D, N2, act, rms, ls):
+    """The residual GEMM with the staged (TMA-loaded, fp32-added) residual leaves per-row partial sums that the next,
+    norm-folded GEMM finishes in its epilogue: same result as the statistics-kernel path and as fp32 torch."""
+    from vla_adapter_b200 import ops
+
+    a = _randn(rows, K1, seed=41)
+    W1 = _randn(D, K1, scale=K1 ** -0.5, seed=42)
+    b1 = torch.randn(D, device="cuda") * 0.1
+    cs1 = (torch.rand(D, device="cuda") + 0.5) if ls else None
+    x0 = _randn(rows, D, seed=43) * 2 + 0.7           # a residual stream with a DC offset
+    nw = torch.rand(D, device="cuda") + 0.5
+    nb = None if rms else torch.randn(D, device="cuda") * 0.1
+    W2 = _randn(N2, D, scale=D ** -0.5, seed=44)
+    b2 = None if act == "swiglu" else torch.randn(N2, device="cuda") * 0.1
+    x = x0.clone()
+    out, partials = ops.block_tail(a, W1, b1, cs1, x, nw, nb, W2, b2, eps=1e-6, act=act)
+    torch.cuda.synchronize()
+    # (1) the in-place residual update: one rounding of the fp32 sum
+    upd = a.float() @ W1.float().T + b1
+    if ls:
+        upd = upd * cs1
+    x_ref = (x0.float() + upd)
+    assert (x.float() - x_ref).abs().max().item() <= 2 ** -8 * x_ref.abs().max().item() + 1e-3
+    # (2) the partial sums add up to the row sums of the new x (slots nobody owns are zero, none is left NaN)
+    assert torch.isfinite(partials).all()
+    s = partials.sum(1)
+    assert torch.allclose(s[:, 0], x_ref.sum(1), rtol=2e-3, atol=0.5)
+    assert torch.allclose(s[:, 1], (x_ref * x_ref).sum(1), rtol=2e-3)
+    # (3) the norm-folded consumer: against the statistics-kernel path on the same x, and against fp32 torch
+    out_k = ops.norm_linear(x, nw, nb, W2, b2, eps=1e-6, act=act)
+    xf = x.float()
+    if rms:
+        xn = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)) * nw
+    else:
+        xn = torch.nn.functional.layer_norm(xf, (D,), nw, nb, 1e-6)
+    y = xn @ W2.float().T
+    if b2 is not None:
+        y = y + b2
+    if act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    elif act == "swiglu":
+        y = y.view(rows, N2 // 32, 2, 16)
+        y = (torch.nn.functional.silu(y[:, :, 0]) * y[:, :, 1]).reshape(rows, N2 // 2)
+    assert _rel(out, y) < 1e-2
+    assert _rel(out, out_k.float()) < 4e-3

@@ -61,6 +61,9 @@ SIGNATURES = {
     "vla_op_fold_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vla_op_norm_gemm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "vla_op_block_tail": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int,
+                                  c_void_p, c_void_p]),
     "vla_op_attention": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_int, c_void_p]),
     "vla_op_gemm_rope": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,

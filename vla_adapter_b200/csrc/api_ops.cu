@@ -99,6 +99,28 @@ int vla_op_norm_gemm(const void* x, int rows, int ldx, const void* W, int ldw, i
   return rc ? fail(rc, err) : 0;
 }
 
+int vla_op_block_tail(const void* a, int lda, int rows, const void* W1, int ldw1, int K1, void* x, int D,
+                      const float* bias1, const float* colscale1, const void* W2, int ldw2, int N2, void* out, int ldo,
+                      const float* bias2, const float* colsum2, int rms, float eps, int act, float* partials,
+                      void* stream) {
+  const char* err = nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  vla::GemmArgs g;  // x += colscale1 * (a @ W1^T + bias1), leaving the row statistics of the new x
+  g.A = static_cast<const __nv_bfloat16*>(a); g.lda = lda; g.rows = rows;
+  g.W = static_cast<const __nv_bfloat16*>(W1); g.ldw = ldw1; g.N = D; g.K = K1;
+  g.C = static_cast<__nv_bfloat16*>(x); g.ldc = D; g.bias = bias1; g.colscale = colscale1;
+  g.resid = static_cast<const __nv_bfloat16*>(x); g.ldr = D; g.stat_out = partials; g.resid_staged = 1;
+  int rc = vla::gemm_launch(g, s, &err);
+  if (rc) return fail(rc, err);
+  g = vla::GemmArgs();  // out = act(Linear(Norm(x))) with the norm folded into W2 and the statistics from the partials
+  g.A = static_cast<const __nv_bfloat16*>(x); g.lda = D; g.rows = rows;
+  g.W = static_cast<const __nv_bfloat16*>(W2); g.ldw = ldw2; g.N = N2; g.K = D;
+  g.C = static_cast<__nv_bfloat16*>(out); g.ldc = ldo; g.bias = bias2; g.act = act;
+  g.stat_in = partials; g.stat_dim = D; g.stat_eps = eps; g.stat_rms = rms; g.colsum = rms ? nullptr : colsum2;
+  rc = vla::gemm_launch(g, s, &err);
+  return rc ? fail(rc, err) : 0;
+}
+
 int vla_op_rmsnorm(const void* x, int rows, int dim, int ldx, const float* w, float eps, void* y, int ldy,
                    void* stream) {
   const char* err = nullptr;

@@ -188,6 +188,13 @@ struct vla_engine {
   // LayerNorm / RMSNorm in front of a GEMM folded into that GEMM (weights pre-scaled at finalize, per-row statistics
   // applied in its epilogue): the normalised activations are never written.  VLA_NO_NORM_FOLD=1 keeps the norm kernels.
   int fold_norms = 1;
+  // ... and, optionally (VLA_STAT_FUSE=1), the row statistics of those norms taken from partial sums the PRODUCING
+  // GEMM leaves in its epilogue (gemm.cuh: stat_out / stat_in) instead of a statistics kernel per norm: 143 of the 146
+  // statistics launches of a step disappear.  OFF by default: measured on B200 at bs=64 (same box, A/B/A/B) the step
+  // takes 83.8 ms either way - the chip is ENERGY-limited there (every GEMM's in-kernel SM clock drops from ~1250 to
+  // ~1130 MHz once the low-power statistics kernels no longer give the power budget a rest), the staged-residual
+  // epilogue it needs costs what the statistics kernels cost, and at bs=1 its longer epilogue adds 0.37 ms.
+  int stat_fuse = 0;
   float* l_stats = nullptr;
   // segment timing (vla_segment_times): events at the subsystem boundaries of the last EAGER forward
   int seg_on = 0;
@@ -380,7 +387,12 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
     const VitBlock& k = t.blocks[i];
     const bool last = (i == nblk - 1);
     vla::GemmArgs g;
-    if (e->fold_norms) {  // norm1 lives in wqkv / bqkv / cs_qkv; only the row statistics are computed here
+    if (e->fold_norms && e->stat_fuse) {
+      // norm1 lives in wqkv / bqkv / cs_qkv; the row statistics come from the partial sums the previous block's fc2
+      // GEMM left (block 0: from one statistics pass over the patch-embed output)
+      if (i == 0) CK(vla::row_stats_launch(x, M, D, D, 0, VIT_EPS, ws.stats, s, &_err, vla::STAT_SLOTS));
+      g.A = x; g.stat_in = ws.stats; g.stat_dim = D; g.stat_eps = VIT_EPS; g.colsum = k.cs_qkv;
+    } else if (e->fold_norms) {  // norm1 lives in wqkv / bqkv / cs_qkv; only the row statistics are computed here
       CK(vla::row_stats_launch(x, M, D, D, 0, VIT_EPS, ws.stats, s, &_err));
       g.A = x; g.row_stats = ws.stats; g.colsum = k.cs_qkv;
     } else {
@@ -394,9 +406,12 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
     g = vla::GemmArgs();
     g.A = ws.attn; g.lda = D; g.rows = M; g.W = k.wproj; g.ldw = D; g.N = D; g.K = D;
     g.C = x; g.ldc = D; g.bias = k.bproj; g.colscale = k.ls1; g.resid = x; g.ldr = D;
+    if (e->stat_fuse) g.stat_out = ws.stats;  // statistics of the new x for norm2, from this GEMM's epilogue
     CK(vla::gemm_launch(g, s, &_err));
     g = vla::GemmArgs();
-    if (e->fold_norms) {
+    if (e->fold_norms && e->stat_fuse) {
+      g.A = x; g.stat_in = ws.stats; g.stat_dim = D; g.stat_eps = VIT_EPS; g.colsum = k.cs_fc1;
+    } else if (e->fold_norms) {
       CK(vla::row_stats_launch(x, M, D, D, 0, VIT_EPS, ws.stats, s, &_err));
       g.A = x; g.row_stats = ws.stats; g.colsum = k.cs_fc1;
     } else {
@@ -411,6 +426,7 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
     if (!last) {
       g.A = ws.h; g.lda = F; g.rows = M;
       g.C = x; g.ldc = D; g.resid = x; g.ldr = D;
+      if (e->stat_fuse) g.stat_out = ws.stats;  // ... and of the block's output for the next block's norm1
     } else {
       // Output block: only the patch rows (prefix stripped, film_vit_wrapper.py:162) go to the
       // feature-concatenated buffer (modeling_prismatic.py:233, 237).
@@ -526,7 +542,11 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     const bf16* xin = e->hid[l];
     bf16* xout = (l == NL - 1) ? e->l_tmp : e->hid[l + 1];
     vla::GemmArgs g;
-    if (e->fold_norms) {
+    if (e->fold_norms && e->stat_fuse) {
+      // sum x^2 of every row comes from the previous layer's down-projection epilogue (layer 0: one statistics pass)
+      if (l == 0) CK(vla::row_stats_launch(xin, M, D_LLM, D_LLM, 1, LLM_EPS, e->l_stats, s, &_err, vla::STAT_SLOTS));
+      g.A = xin; g.stat_in = e->l_stats; g.stat_dim = D_LLM; g.stat_eps = LLM_EPS; g.stat_rms = 1;
+    } else if (e->fold_norms) {
       CK(vla::row_stats_launch(xin, M, D_LLM, D_LLM, 1, LLM_EPS, e->l_stats, s, &_err));
       g.A = xin; g.row_stats = e->l_stats;
     } else {
@@ -551,9 +571,12 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     g = vla::GemmArgs();
     g.A = e->l_attn; g.lda = D_LLM; g.rows = M; g.W = w.wo; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
     g.C = xout; g.ldc = D_LLM; g.resid = xin; g.ldr = D_LLM;
+    if (e->stat_fuse) g.stat_out = e->l_stats;
     CK(vla::gemm_launch(g, s, &_err));
     g = vla::GemmArgs();
-    if (e->fold_norms) {
+    if (e->fold_norms && e->stat_fuse) {
+      g.A = xout; g.stat_in = e->l_stats; g.stat_dim = D_LLM; g.stat_eps = LLM_EPS; g.stat_rms = 1;
+    } else if (e->fold_norms) {
       CK(vla::row_stats_launch(xout, M, D_LLM, D_LLM, 1, LLM_EPS, e->l_stats, s, &_err));
       g.A = xout; g.row_stats = e->l_stats;
     } else {
@@ -566,6 +589,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     g = vla::GemmArgs();
     g.A = e->l_act; g.lda = I_LLM; g.rows = M; g.W = w.wdown; g.ldw = I_LLM; g.N = D_LLM; g.K = I_LLM;
     g.C = xout; g.ldc = D_LLM; g.resid = xout; g.ldr = D_LLM;
+    if (e->stat_fuse && l + 1 < NL) g.stat_out = e->l_stats;
     CK(vla::gemm_launch(g, s, &_err));
     if (small && l + 1 < NL) {  // hid[l+1] is final: its policy K|V projections start now, beside the next LLM layer
       rc = policy_kv_from_llm(e, l, e->hid[l + 1], B, L, prompt_len, s, s2);
@@ -664,6 +688,8 @@ int vla_create(const vla_cfg* cfg, vla_engine** out) {
   }
   if (const char* ng = getenv("VLA_NO_GRAPH")) e->use_graphs = atoi(ng) ? 0 : 1;
   if (const char* nf = getenv("VLA_NO_NORM_FOLD")) e->fold_norms = atoi(nf) ? 0 : 1;
+  if (const char* sf = getenv("VLA_STAT_FUSE")) e->stat_fuse = atoi(sf) ? 1 : 0;
+  if (!e->fold_norms) e->stat_fuse = 0;
   const vla_cfg& c = e->cfg;
   if (c.n_images < 1 || c.n_images > 3) return e->fail(VLA_ERR_INVALID, "n_images must be 1..3");
   if (c.chunk_len < 1 || c.chunk_len > 32) return e->fail(VLA_ERR_INVALID, "chunk_len must be 1..32");
@@ -927,7 +953,7 @@ int vla_finalize(vla_engine* e) {
       e->tw[t].col = e->dalloc<bf16>(slabs * 256 * KP);
       e->tw[t].x = e->dalloc<bf16>(Mv * D);
       e->tw[t].xn = e->dalloc<bf16>(Mv * D);
-      e->tw[t].stats = e->dalloc<float>(2 * Mv);
+      e->tw[t].stats = e->dalloc<float>(2 * vla::STAT_SLOTS * Mv);
       e->tw[t].qkv = e->dalloc<bf16>(Mv * 3 * D);
       e->tw[t].attn = e->dalloc<bf16>(Mv * D);
       e->tw[t].h = e->dalloc<bf16>(Mv * F);
@@ -939,7 +965,7 @@ int vla_finalize(vla_engine* e) {
     for (int i = 0; i <= c.llm_layers; ++i) e->hid.push_back(e->dalloc<bf16>(Ml * D_LLM));
     e->l_tmp = e->dalloc<bf16>(Ml * D_LLM);
     e->l_xn = e->dalloc<bf16>(Ml * D_LLM);
-    e->l_stats = e->dalloc<float>(2 * Ml);
+    e->l_stats = e->dalloc<float>(2 * vla::STAT_SLOTS * Ml);
     e->l_qkv = e->dalloc<bf16>(Ml * QKV_LLM);
     e->l_attn = e->dalloc<bf16>(Ml * D_LLM);
     e->l_act = e->dalloc<bf16>(Ml * I_LLM);

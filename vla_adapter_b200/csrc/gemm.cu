@@ -41,9 +41,17 @@ constexpr int GEMM_THREADS = 352;          // warp 0 TMA, warp 1 MMA, warps 2-9 
 constexpr int GEMM_WORK_WARPS = 10;
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB per stage
+// Shared memory: [operand ring | epilogue staging | barriers].  Ring + staging are 224 KB in both layouts:
+//   plain epilogue          : 192 KB ring + 8 warps x 2 boxes (32 rows x 64 B) - a box is written, then TMA-stored
+//   staged-residual epilogue: 160 KB ring + 8 warps x 4 boxes - the residual box is TMA-LOADED into the box two chunks
+//                             ahead, the epilogue adds in fp32 in place and TMA-stores the same box
 constexpr uint32_t RING_BYTES = 192 * 1024;
-constexpr uint32_t STAGING_BYTES = EPI_WARPS * 2 * 2048;  // per epilogue warp: 2 x (32 rows x 64 B)
-constexpr uint32_t SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t RING_BYTES_STAGED = 160 * 1024;
+constexpr uint32_t STAGING_BYTES = EPI_WARPS * 2 * 2048;
+constexpr uint32_t BAR_OFFSET = RING_BYTES + STAGING_BYTES;  // = RING_BYTES_STAGED + EPI_WARPS * 4 * 2048
+constexpr uint32_t SMEM_BYTES = BAR_OFFSET + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int RES_BUFS = 4;      // staging boxes per epilogue warp in the staged-residual layout
+constexpr int RES_AHEAD = 2;     // residual boxes in flight ahead of the chunk being finished
 constexpr uint32_t TMEM_COLS = 512;        // two accumulators of up to 256 columns
 constexpr int MAX_STAGES = 8;
 
@@ -65,6 +73,13 @@ struct GemmDev {
   int rope_cols, rope_S, rope_ld;
   const float2* row_stats;  // normalisation of A folded into the epilogue (see GemmArgs)
   const float* colsum;
+  int resid_tma;            // 1: the residual arrives through mapR into the staging boxes (staged-residual epilogue)
+  uint32_t ring_bytes;      // operand ring size of the layout in use
+  // row statistics without a statistics kernel (see GemmArgs::stat_out / stat_in)
+  float2* stat_out;
+  const float2* stat_in;
+  float stat_inv_dim, stat_eps;
+  int stat_rms;
   // profiling only (vla_profile_gemm): CTA 0's monitor warp writes {globaltimer, clock64} at its start and end, which
   // gives the kernel's duration AND the SM clock it ran at inside a real step (ncu serialises and cannot show that)
   unsigned long long* prof;
@@ -123,7 +138,8 @@ __device__ __noinline__ void gemm_monitor(uint32_t done_bar, uint32_t note_base,
 template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                         const __grid_constant__ CUtensorMap mapC, const GemmDev p) {
+                         const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapR,
+                         const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -134,9 +150,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
   const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn / CG) * BK * 2;  // this CTA's share of the B tile
   const uint32_t stage_bytes = A_BYTES + b_bytes;
-  const uint32_t staging_base = smem_base + RING_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + STAGING_BYTES);
-  const uint32_t bar_base = smem_base + RING_BYTES + STAGING_BYTES;
+  const uint32_t staging_base = smem_base + p.ring_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+  const uint32_t bar_base = smem_base + BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
@@ -144,6 +160,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
   const uint32_t done_bar = bar_base + 8u * (2 * MAX_STAGES + 5);        // watchdog: every working warp arrives at its end
   const uint32_t note_base = bar_base + 8u * (2 * MAX_STAGES + 6);       // watchdog: one "last wait" word per warp
+  auto res_bar = [&](int e, int i) { return bar_base + 256u + 8u * (e * RES_BUFS + i); };  // residual box landed
 
   // Warp index broadcast with shfl so the compiler knows the role branches are warp-uniform: the MMA warp's
   // descriptor arithmetic then stays on the uniform datapath and tcgen05.mma issues at the hardware rate
@@ -155,6 +172,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     tma_prefetch_desc(&mapC);
+    if (p.resid_tma) tma_prefetch_desc(&mapR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -164,6 +182,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       mbar_init(tempty_bar(a), EPI_WARPS * CG);  // the leader's barrier collects the epilogue warps of both CTAs
     }
     mbar_init(done_bar, GEMM_WORK_WARPS);
+    if (p.resid_tma)
+      for (int i = 0; i < EPI_WARPS * RES_BUFS; ++i) mbar_init(res_bar(0, i), 1);
     mbar_fence_init();
     fence_proxy_async();
   }
@@ -290,8 +310,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     const int w0 = ((p.bn >> 1) + 31) & ~31;
     const int wcols = half ? p.bn - w0 : w0;
     const int wcol0 = half ? w0 : 0;
-    const uint32_t buf0 = staging_base + static_cast<uint32_t>(e) * 4096u;
+    const uint32_t buf0 = staging_base + static_cast<uint32_t>(e) * (p.resid_tma ? RES_BUFS * 2048u : 4096u);
     int buf = 0;
+    uint32_t res_g = 0;  // staged residual: running chunk counter of this warp (box = res_g % RES_BUFS, parity from res_g)
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool swiglu = p.act == ACT_SWIGLU;
@@ -310,6 +331,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
       const int n0 = n_idx * p.bn + wcol0;
       float2 rst = make_float2(1.f, 0.f);  // this thread's row: (rstd, -mean * rstd)
       if (p.row_stats && r0 + lane < p.rows) rst = __ldg(p.row_stats + r0 + lane);
+      if (p.stat_in && r0 + lane < p.rows) {
+        // the producing GEMM left STAT_SLOTS partial (sum x, sum x^2) pairs per row: finish the statistics here
+        const float4* sp = reinterpret_cast<const float4*>(p.stat_in + static_cast<long long>(r0 + lane) * STAT_SLOTS);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < STAT_SLOTS / 2; ++k) {
+          const float4 t = __ldg(sp + k);
+          s1 += t.x + t.z;
+          s2 += t.y + t.w;
+        }
+        if (p.stat_rms) {
+          rst = make_float2(rsqrtf(s2 * p.stat_inv_dim + p.stat_eps), 0.f);
+        } else {
+          const float mean = s1 * p.stat_inv_dim;
+          const float rstd = rsqrtf(fmaxf(s2 * p.stat_inv_dim - mean * mean, 0.f) + p.stat_eps);
+          rst = make_float2(rstd, -mean * rstd);
+        }
+      }
+      // staged residual: chunk i of this tile uses box (res_g + i) % RES_BUFS; the first RES_AHEAD boxes are requested
+      // before the wait for the accumulator, so they land under the tile's mainloop
+      const bool res_live = p.resid_tma && live && n0 < p.N;
+      auto res_fetch = [&](int i) {  // lane 0: residual box of chunk i -> its staging box
+        const int c0 = n0 + i * 32;
+        if (i * 32 < wcols && c0 < p.N) {
+          const uint32_t g = res_g + static_cast<uint32_t>(i);
+          tma_store_wait_read<1>();  // the store that last used this box (RES_BUFS chunks ago) has read it
+          mbar_arrive_expect_tx(res_bar(e, g % RES_BUFS), 2048u);
+          tma_load_3d(buf0 + (g % RES_BUFS) * 2048u, &mapR, res_bar(e, g % RES_BUFS), c0, r0, b);
+        }
+      };
+      if (res_live && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < RES_AHEAD; ++i) res_fetch(i);
+      }
+      float2 st_sum = make_float2(0.f, 0.f), st_sq = make_float2(0.f, 0.f);  // this row's partial sums (stat_out)
 
       wd_note(my_note, VLA_WD_NOTE(4, acc, acc_phase, tile));
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);
@@ -445,7 +501,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 f[2 * q + 1] = __fmul2_rn(f[2 * q + 1], make_float2(sv.z, sv.w));
               }
             }
-            if (p.resid) {  // out-of-place residual: this thread's row, 32 columns = four 16-byte loads
+            if (p.resid_tma) {
+              // staged residual: the box landed in shared memory (64B-swizzled like the output box); add in fp32
+              const uint32_t g = res_g + static_cast<uint32_t>(ch >> 5);
+              const uint32_t box = buf0 + (g % RES_BUFS) * 2048u;
+              if (lane == 0) res_fetch((ch >> 5) + RES_AHEAD);
+              __syncwarp();
+              mbar_wait(res_bar(e, g % RES_BUFS), (g / RES_BUFS) & 1u);
+              const uint32_t row_addr = box + lane * 64;
+              const int sw = (lane >> 1) & 3;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t r0w, r1w, r2w, r3w;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r0w), "=r"(r1w), "=r"(r2w), "=r"(r3w)
+                             : "r"(row_addr + ((q ^ sw) << 4)));
+                f[4 * q] = __fadd2_rn(f[4 * q], unpack_bf16(r0w));
+                f[4 * q + 1] = __fadd2_rn(f[4 * q + 1], unpack_bf16(r1w));
+                f[4 * q + 2] = __fadd2_rn(f[4 * q + 2], unpack_bf16(r2w));
+                f[4 * q + 3] = __fadd2_rn(f[4 * q + 3], unpack_bf16(r3w));
+              }
+            } else if (p.resid) {  // out-of-place residual: this thread's row, 32 columns = four 16-byte loads
               const int rr = r0 + lane;
               if (rr < p.rows) {
                 const __nv_bfloat16* rp = p.resid + b * p.r_bs + static_cast<long long>(rr) * p.ldr + c0;
@@ -463,10 +539,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = pack_bf16(f[j].x, f[j].y);
-            store_box(&mapC, buf0 + buf * 2048u, lane, o, c0, r0, b, p.accumulate);
-            buf ^= 1;
+            if (p.stat_out) {  // partial row sums of what was just produced (columns past N hold zeros: bias / TMA fill)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const bool in_n = c0 + 2 * j < p.N;
+                const float2 u = in_n ? f[j] : make_float2(0.f, 0.f);
+                st_sum = __fadd2_rn(st_sum, u);
+                st_sq = __ffma2_rn(u, u, st_sq);
+              }
+            }
+            if (p.resid_tma) {
+              // in place: the box the residual arrived in is rewritten and stored (no other store is pending on it)
+              const uint32_t g = res_g + static_cast<uint32_t>(ch >> 5);
+              const uint32_t box = buf0 + (g % RES_BUFS) * 2048u;
+              const uint32_t row_addr = box + lane * 64;
+              const int sw = (lane >> 1) & 3;
+              __syncwarp();
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((u ^ sw) << 4)), "r"(o[4 * u]),
+                             "r"(o[4 * u + 1]), "r"(o[4 * u + 2]), "r"(o[4 * u + 3])
+                             : "memory");
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&mapC, box, c0, r0, b);
+                tma_store_commit();
+              }
+            } else {
+              store_box(&mapC, buf0 + buf * 2048u, lane, o, c0, r0, b, p.accumulate);
+              buf ^= 1;
+            }
+          }
+          if (p.resid_tma) {  // chunks of this tile that were consumed
+            int used = 0;
+            for (int ch = 0; ch < wcols && n0 + ch < p.N; ch += 32) ++used;
+            res_g += static_cast<uint32_t>(used);
           }
         }
+      }
+      if (p.stat_out && r0 + lane < p.rows) {
+        // slot of this (column tile, half); a sub-tile that lies past N writes zeros; the first warp of a row also
+        // clears the slots no column tile owns, so that the consumer can always sum STAT_SLOTS of them
+        float2* sp = p.stat_out + static_cast<long long>(r0 + lane) * STAT_SLOTS;
+        sp[n_idx * 2 + half] = make_float2(st_sum.x + st_sum.y, st_sq.x + st_sq.y);
+        if (n_idx == 0 && half == 0)
+          for (int k = p.tiles_n * 2; k < STAT_SLOTS; ++k) sp[k] = make_float2(0.f, 0.f);
       }
       tc_fence_before();
       __syncwarp();
@@ -669,9 +787,15 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     if (err) *err = "gemm: SwiGLU epilogue needs N % 64 == 0 and takes no residual";
     return -1;
   }
-  if ((a.row_stats || a.colsum) && (a.batches != 1 || !a.row_stats || (swiglu && a.colsum) ||
-                                    (reinterpret_cast<uintptr_t>(a.row_stats) & 7))) {
-    if (err) *err = "gemm: a folded norm needs row_stats, one row view, and no mean term with SwiGLU";
+  if ((a.row_stats || a.colsum || a.stat_in) &&
+      (a.batches != 1 || (!a.row_stats && !a.stat_in) || (a.row_stats && a.stat_in) || (swiglu && a.colsum) ||
+       (reinterpret_cast<uintptr_t>(a.row_stats) & 7) || (reinterpret_cast<uintptr_t>(a.stat_in) & 15) ||
+       (a.stat_in && a.stat_dim <= 0))) {
+    if (err) *err = "gemm: a folded norm needs row_stats or stat_in (not both), one row view, and no mean term with SwiGLU";
+    return -1;
+  }
+  if (a.stat_out && (a.batches != 1 || swiglu || a.rope_cols > 0 || (reinterpret_cast<uintptr_t>(a.stat_out) & 15))) {
+    if (err) *err = "gemm: stat_out needs one row view and the plain epilogue";
     return -1;
   }
   static PerDeviceFlag attr_flag;  // the shared-memory opt-in is per device
@@ -718,6 +842,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     for (int i = 0; i < 5; ++i) {
       const int c = cands[i];
       if (swiglu && (c & 127)) continue;  // a SwiGLU output box needs 64 accumulator columns per warp
+      if (a.stat_out && 2 * ((a.N + c - 1) / c) > STAT_SLOTS) continue;  // one statistics slot per column tile half
       const long long tiles = static_cast<long long>(tiles_m) * ((a.N + c - 1) / c);
       const long long rounds = (tiles + sms - 1) / sms;
       // measured fixed cost per tile, in columns: ~96 for single CTAs, ~64 for CTA pairs (sig.fc2 / llm.down then take
@@ -745,9 +870,28 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   // residual rows itself and adds in fp32 before the bf16 store.  (A broadcast residual - batch stride 0, the ViT
   // position embedding - is pre-copied: its rows are shared by every batch.)
   const bool in_place = a.resid && a.resid == a.C && a.ldr == a.ldc && (a.batches == 1 || a.r_batch_stride == a.c_batch_stride);
-  const bool fused_resid = a.resid && !in_place && (a.batches == 1 || a.r_batch_stride != 0);
-  bool accumulate = in_place;
-  if (a.resid && !in_place && !fused_resid) {
+  // Staged residual: in place or out of place, the residual box comes in by TMA and is added in fp32 - one rounding
+  // instead of the reduce-add's two, no strided per-thread row loads, and the epilogue sees the FINAL values (which is
+  // what stat_out needs).  Used when asked for (resid_staged = 1, stat_out) or with VLA_GEMM_STAGED_RESID=1; the default
+  // stays the reduce-add / direct-read epilogue, which measures the same at bs=64 and is shorter at bs=1 (one tile per
+  // CTA: the epilogue's latency is exposed there).
+  static const int staged_env = [] {
+    const char* e = getenv("VLA_GEMM_STAGED_RESID");
+    return e ? atoi(e) : 0;
+  }();
+  const bool can_stage = a.resid && !pack && !swiglu && a.rope_cols == 0 && (a.batches == 1 || a.r_batch_stride != 0);
+  const bool staged = can_stage && (a.resid_staged < 0 ? (staged_env != 0 || a.stat_out != nullptr) : a.resid_staged != 0);
+  if (a.stat_out && a.resid && !staged) {
+    if (err) *err = "gemm: stat_out with a residual needs the staged-residual epilogue";
+    return -1;
+  }
+  if (a.stat_out && 2 * ((a.N + bn - 1) / bn) > STAT_SLOTS) {
+    if (err) *err = "gemm: stat_out: too many column tiles for STAT_SLOTS (tile width too small for this N)";
+    return -1;
+  }
+  const bool fused_resid = a.resid && !staged && !in_place && (a.batches == 1 || a.r_batch_stride != 0);
+  bool accumulate = in_place && !staged;
+  if (a.resid && !staged && !in_place && !fused_resid) {
     const long long total = static_cast<long long>(a.batches) * a.rows * (a.N >> 3);
     launch_kernel(copy_view_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 
         a.resid, a.r_batch_stride, a.ldr, a.C, a.c_batch_stride, a.ldc, a.rows, a.batches, a.N);
@@ -766,7 +910,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.tiles_n = (a.N + bn - 1) / bn;
   p.bn = bn;
   const uint32_t stage_bytes = A_BYTES + static_cast<uint32_t>(bn / cg) * BK * 2;
-  p.stages = static_cast<int>(RING_BYTES / stage_bytes);
+  p.ring_bytes = staged ? RING_BYTES_STAGED : RING_BYTES;
+  p.resid_tma = staged ? 1 : 0;
+  p.stages = static_cast<int>(p.ring_bytes / stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.bias = a.bias;
   p.colscale = a.colscale;
@@ -782,8 +928,13 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   p.row_stats = reinterpret_cast<const float2*>(a.row_stats);
   p.colsum = a.colsum;
   p.prof = nullptr;
+  p.stat_out = reinterpret_cast<float2*>(a.stat_out);
+  p.stat_in = reinterpret_cast<const float2*>(a.stat_in);
+  p.stat_inv_dim = a.stat_dim > 0 ? 1.0f / static_cast<float>(a.stat_dim) : 0.f;
+  p.stat_eps = a.stat_eps;
+  p.stat_rms = a.stat_rms;
 
-  CUtensorMap mA, mB, mC;
+  CUtensorMap mA, mB, mC, mR;
   const uint64_t a_bs = a.batches > 1 ? static_cast<uint64_t>(a.a_batch_stride)
                                       : static_cast<uint64_t>(a.rows) * a.lda;
   const uint64_t c_bs = a.batches > 1 ? static_cast<uint64_t>(a.c_batch_stride)
@@ -799,6 +950,14 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
                    c_box_batches)) {
     if (err) *err = "gemm: cuTensorMapEncodeTiled failed";
     return -4;
+  }
+  mR = mC;
+  if (staged && !in_place) {  // the residual lives elsewhere: its own (column, row, batch) view, same 32 x 32 boxes
+    const uint64_t r_bs = a.batches > 1 ? static_cast<uint64_t>(a.r_batch_stride) : static_cast<uint64_t>(a.rows) * a.ldr;
+    if (!make_map_3d(&mR, a.resid, n_out, a.rows, a.batches, a.ldr, r_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, 1)) {
+      if (err) *err = "gemm: cuTensorMapEncodeTiled failed (residual view)";
+      return -4;
+    }
   }
 
   const int total = p.tiles_m * p.tiles_n;
@@ -821,8 +980,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
     cudaEventCreate(&rec.e1);
     cudaEventRecord(rec.e0, stream);
   }
-  if (cg == 2) launch_kernel_cluster(2, gemm_bf16_tcgen05_kernel<2>, dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, stream, mA, mB, mC, p);
-  else launch_kernel(gemm_bf16_tcgen05_kernel<1>, dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, stream, mA, mB, mC, p);
+  if (cg == 2) launch_kernel_cluster(2, gemm_bf16_tcgen05_kernel<2>, dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, stream, mA, mB, mC, mR, p);
+  else launch_kernel(gemm_bf16_tcgen05_kernel<1>, dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, stream, mA, mB, mC, mR, p);
   if (prof) {
     cudaEventRecord(rec.e1, stream);
     std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -8,6 +8,11 @@ namespace vla {
 
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SWIGLU = 3 };
 
+// Row statistics without a statistics kernel: a GEMM that writes rows of a residual stream leaves, per row, STAT_SLOTS
+// partial (sum x, sum x^2) pairs (one per column tile half, unused slots zero); the GEMM that consumes those rows
+// behind a folded LayerNorm / RMSNorm sums the slots in its epilogue.  [rows][STAT_SLOTS] float2.
+constexpr int STAT_SLOTS = 12;
+
 // C[b, r, n] = epi( sum_k A[b, r, k] * W[n, k] )      (nn.Linear convention: W is [N, K], K contiguous)
 //
 // A and C are 3-D *views*: `batches` slabs of `rows` rows each, slab b starting at
@@ -53,6 +58,19 @@ struct GemmArgs {
   // whose mean term is absent).  One row view only (batches == 1).
   const float* row_stats = nullptr;  // [rows][2] fp32
   const float* colsum = nullptr;     // [N] fp32
+  // The same folded norm with the statistics taken from the PRODUCER's partial sums instead of row_stats:
+  // stat_in = [rows][STAT_SLOTS] float2 written by an earlier gemm_launch with stat_out; the epilogue computes
+  // mean = sum x / stat_dim, rstd = rsqrt(E[x^2] - mean^2 + stat_eps)  (stat_rms: rstd = rsqrt(E[x^2] + eps), no mean).
+  const float* stat_in = nullptr;
+  int stat_dim = 0;
+  float stat_eps = 0.f;
+  int stat_rms = 0;
+  // Producer side: partial (sum, sum of squares) of every output row of THIS GEMM (the values before their bf16
+  // rounding), one row view only; restricts the tile width so that 2 * column tiles <= STAT_SLOTS.
+  float* stat_out = nullptr;
+  // Residual handling: -1 auto, 0 legacy (in place: bf16 TMA reduce-add into C; out of place: per-thread row loads),
+  // 1 staged (the residual box is TMA-loaded into the epilogue's staging box, added in fp32, stored by TMA).
+  int resid_staged = -1;
 };
 
 // Returns 0 on success, negative on error (message in *err if non-null).

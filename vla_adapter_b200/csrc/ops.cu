@@ -120,7 +120,8 @@ norm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int batches, long lon
 // rows at a time to keep more loads in flight.
 template <bool RMS>
 __global__ void __launch_bounds__(256, 4)
-row_stats_kernel(const __nv_bfloat16* __restrict__ x, int rows, int dim, int ldx, float eps, float2* __restrict__ stats) {
+row_stats_kernel(const __nv_bfloat16* __restrict__ x, int rows, int dim, int ldx, float eps, float2* __restrict__ stats,
+                 int partial_slots) {
   pdl_wait();
   pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -174,6 +175,13 @@ row_stats_kernel(const __nv_bfloat16* __restrict__ x, int rows, int dim, int ldx
   }
   if (lane < 2 && (lane == 0 || two)) {
     const float s1 = lane ? b1 : a1, s2 = lane ? b2 : a2, pv = lane ? pb : pa;
+    if (partial_slots > 0) {
+      // the producer-GEMM format (gemm.cuh: STAT_SLOTS partial (sum x, sum x^2) pairs per row): everything in slot 0
+      float2* sp = stats + static_cast<long long>(r0 + lane) * partial_slots;
+      sp[0] = make_float2(s1 + dim * pv, s2 + 2.f * pv * s1 + dim * pv * pv);
+      for (int k = 1; k < partial_slots; ++k) sp[k] = make_float2(0.f, 0.f);
+      return;
+    }
     float2 o;
     if (RMS) {
       o = make_float2(rsqrtf(s2 / dim + eps), 0.f);
@@ -512,14 +520,14 @@ int rmsnorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const flo
 }
 
 int row_stats_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, int rms, float eps, float* stats,
-                     cudaStream_t s, const char** err) {
+                     cudaStream_t s, const char** err, int partial_slots) {
   if ((dim & 7) || dim > MAX_VEC_PER_LANE * 256 || (ldx & 7) || (reinterpret_cast<uintptr_t>(stats) & 7)) {
     if (err) *err = "row_stats: dim must be a multiple of 8 and <= 1280";
     return -1;
   }
   const int blocks = (rows + 15) / 16;  // 8 warps x 2 rows
-  if (rms) launch_kernel(row_stats_kernel<true>, dim3(blocks), dim3(256), 0, s, x, rows, dim, ldx, eps, reinterpret_cast<float2*>(stats));
-  else launch_kernel(row_stats_kernel<false>, dim3(blocks), dim3(256), 0, s, x, rows, dim, ldx, eps, reinterpret_cast<float2*>(stats));
+  if (rms) launch_kernel(row_stats_kernel<true>, dim3(blocks), dim3(256), 0, s, x, rows, dim, ldx, eps, reinterpret_cast<float2*>(stats), partial_slots);
+  else launch_kernel(row_stats_kernel<false>, dim3(blocks), dim3(256), 0, s, x, rows, dim, ldx, eps, reinterpret_cast<float2*>(stats), partial_slots);
   return check_launch(err);
 }
 

@@ -20,8 +20,10 @@ int layernorm_launch_3d(const __nv_bfloat16* x, int rows, int batches, long long
 // Qwen2RMSNorm (transformers Qwen2RMSNorm.forward): bf16(x * rsqrt(mean x^2 + eps)) * w.
 // Norm folded into the next GEMM (gemm.cuh: GemmArgs::row_stats): per-row (rstd, -mean * rstd) of x, and the
 // one-time fold of the norm's weight / bias into that GEMM's W / bias (+ the column sums its epilogue needs).
+// partial_slots > 0: instead of (rstd, -mean * rstd) write the producer-GEMM format of gemm.cuh (STAT_SLOTS partial
+// (sum x, sum x^2) pairs per row, everything in slot 0) - for the first layer of a stack, whose rows no GEMM produced.
 int row_stats_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, int rms, float eps, float* stats,
-                     cudaStream_t s, const char** err);
+                     cudaStream_t s, const char** err, int partial_slots = 0);
 int fold_norm_launch(__nv_bfloat16* W, int N, int K, int ldw, const float* g, const float* b, float* bias,
                      float* colsum, cudaStream_t s, const char** err);
 int rmsnorm_launch(const __nv_bfloat16* x, int rows, int dim, int ldx, const float* w, float eps,

@@ -98,6 +98,28 @@ def norm_linear(x, norm_w, norm_b, W, bias, eps=1e-6, act="none"):
     return out
 
 
+def block_tail(a, W1, bias1, colscale1, x, norm_w, norm_b, W2, bias2, eps=1e-6, act="none"):
+    """x += colscale1 * (a @ W1.T + bias1) in place, then act(Linear(Norm(x))) with the row statistics taken from the
+    first GEMM's epilogue (no statistics kernel).  Returns (out, partials); norm_b=None selects RMSNorm."""
+    _need_cuda(a, W1, x, norm_w, W2)
+    rows, K1 = a.shape
+    D, N2 = x.shape[1], W2.shape[0]
+    rms = norm_b is None
+    Wf = W2.clone()
+    bf = bias2.clone() if bias2 is not None else (None if rms else torch.zeros(N2, dtype=torch.float32, device=x.device))
+    colsum = torch.empty(N2, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.vla_op_fold_norm(_ptr(Wf), N2, D, Wf.stride(0), _ptr(norm_w), None if rms else _ptr(norm_b),
+                                    None if bf is None else _ptr(bf), _ptr(colsum), _stream()))
+    out = torch.empty((rows, N2 // 2 if act == "swiglu" else N2), dtype=torch.bfloat16, device=x.device)
+    partials = torch.full((rows, 12, 2), float("nan"), dtype=torch.float32, device=x.device)
+    _lib.check(lib.vla_op_block_tail(_ptr(a), a.stride(0), rows, _ptr(W1), W1.stride(0), K1, _ptr(x), D, _ptr(bias1),
+                                     _ptr(colscale1), _ptr(Wf), Wf.stride(0), N2, _ptr(out), out.stride(0),
+                                     None if bf is None else _ptr(bf), _ptr(colsum), int(rms), eps, ACT[act],
+                                     _ptr(partials), _stream()))
+    return out, partials
+
+
 def attention(qkv, B, S, n_heads, n_kv_heads, hd, causal):
     """qkv: (B*S, (n_heads + 2*n_kv_heads) * hd) packed [q | k | v]."""
     _need_cuda(qkv)
