@@ -364,12 +364,27 @@ void build_tower(vla_engine* e, Tower& t, const std::string& pfx, bool is_dino, 
     if (_rc) return e->fail(_rc, _err ? _err : "kernel launch failed"); \
   } while (0)
 
+// Where the row statistics of a folded norm come from:
+//   STATS_KERNEL  one row_stats launch per norm; the residual GEMMs add in place by TMA reduce-add (large batches:
+//                 the cheapest in energy, which is what bounds the bs=64 step)
+//   STATS_STAGED  partial sums from the producing GEMM with the staged-residual epilogue, in place (VLA_STAT_FUSE=1):
+//                 143 launches fewer, the same 83.8 ms at bs=64, +0.37 ms at bs=1
+// (A third form - partial sums from the PLAIN epilogue with the residual GEMMs writing out of place, x -> x' -> x, so
+// that the epilogue sees final values without staging - was built and measured for the launch-bound small batches:
+// bs=1 p50 5.27 ms against 4.93 ms with the statistics kernels.  A 2 us statistics kernel under PDL is cheaper than the
+// longer producer epilogue; removed.)
+enum StatsMode { STATS_KERNEL = 0, STATS_STAGED = 1 };
+static StatsMode stats_mode(const vla_engine* e, int) {
+  return (e->fold_norms && e->stat_fuse) ? STATS_STAGED : STATS_KERNEL;
+}
+
 int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix_u8, int B, int tower_idx,
               cudaStream_t s) {
   const int n = e->cfg.n_images, slabs = B * n, D = t.D, F = t.F;
   const int M = slabs * t.tokens;
   const vla_engine::TowerWs& ws = e->tw[tower_idx];
   bf16* x = ws.x;
+  const StatsMode sm = stats_mode(e, B);
   if (pix_u8) CK(vla::im2col_u8_launch(pix_u8, B, n, tower_idx, e->img_lut, ws.col, s, &_err));
   else CK(vla::im2col_launch(pix, B, n, tower_idx, ws.col, s, &_err));
   if (t.prefix) CK(vla::prefix_tokens_launch(x, slabs, static_cast<long long>(t.tokens) * D, D, t.prefix_rows, t.prefix, s, &_err));
@@ -387,7 +402,7 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
     const VitBlock& k = t.blocks[i];
     const bool last = (i == nblk - 1);
     vla::GemmArgs g;
-    if (e->fold_norms && e->stat_fuse) {
+    if (e->fold_norms && sm != STATS_KERNEL) {
       // norm1 lives in wqkv / bqkv / cs_qkv; the row statistics come from the partial sums the previous block's fc2
       // GEMM left (block 0: from one statistics pass over the patch-embed output)
       if (i == 0) CK(vla::row_stats_launch(x, M, D, D, 0, VIT_EPS, ws.stats, s, &_err, vla::STAT_SLOTS));
@@ -406,10 +421,10 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
     g = vla::GemmArgs();
     g.A = ws.attn; g.lda = D; g.rows = M; g.W = k.wproj; g.ldw = D; g.N = D; g.K = D;
     g.C = x; g.ldc = D; g.bias = k.bproj; g.colscale = k.ls1; g.resid = x; g.ldr = D;
-    if (e->stat_fuse) g.stat_out = ws.stats;  // statistics of the new x for norm2, from this GEMM's epilogue
+    if (sm != STATS_KERNEL) g.stat_out = ws.stats;  // statistics of the new x for norm2, from this GEMM's epilogue
     CK(vla::gemm_launch(g, s, &_err));
     g = vla::GemmArgs();
-    if (e->fold_norms && e->stat_fuse) {
+    if (e->fold_norms && sm != STATS_KERNEL) {
       g.A = x; g.stat_in = ws.stats; g.stat_dim = D; g.stat_eps = VIT_EPS; g.colsum = k.cs_fc1;
     } else if (e->fold_norms) {
       CK(vla::row_stats_launch(x, M, D, D, 0, VIT_EPS, ws.stats, s, &_err));
@@ -426,8 +441,8 @@ int run_tower(vla_engine* e, const Tower& t, const bf16* pix, const uint8_t* pix
     if (!last) {
       g.A = ws.h; g.lda = F; g.rows = M;
       g.C = x; g.ldc = D; g.resid = x; g.ldr = D;
-      if (e->stat_fuse) g.stat_out = ws.stats;  // ... and of the block's output for the next block's norm1
-    } else {
+      if (sm != STATS_KERNEL) g.stat_out = ws.stats;  // ... and of the block's output for the next block's norm1
+      } else {
       // Output block: only the patch rows (prefix stripped, film_vit_wrapper.py:162) go to the
       // feature-concatenated buffer (modeling_prismatic.py:233, 237).
       g.A = ws.h + static_cast<long long>(t.prefix) * F; g.a_batch_stride = static_cast<long long>(t.tokens) * F;
@@ -495,6 +510,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
   const int S = NP + Lext;
   const int M = B * S;
   const int NL = e->cfg.llm_layers;
+  const StatsMode sm = stats_mode(e, B);
 
   const bool seg = e->seg_on && e->seg_ev[0];  // graph capture is off while segment timing is on
   if (seg) cudaEventRecord(e->seg_ev[0], s);
@@ -542,7 +558,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     const bf16* xin = e->hid[l];
     bf16* xout = (l == NL - 1) ? e->l_tmp : e->hid[l + 1];
     vla::GemmArgs g;
-    if (e->fold_norms && e->stat_fuse) {
+    if (e->fold_norms && sm != STATS_KERNEL) {
       // sum x^2 of every row comes from the previous layer's down-projection epilogue (layer 0: one statistics pass)
       if (l == 0) CK(vla::row_stats_launch(xin, M, D_LLM, D_LLM, 1, LLM_EPS, e->l_stats, s, &_err, vla::STAT_SLOTS));
       g.A = xin; g.stat_in = e->l_stats; g.stat_dim = D_LLM; g.stat_eps = LLM_EPS; g.stat_rms = 1;
@@ -571,10 +587,10 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     g = vla::GemmArgs();
     g.A = e->l_attn; g.lda = D_LLM; g.rows = M; g.W = w.wo; g.ldw = D_LLM; g.N = D_LLM; g.K = D_LLM;
     g.C = xout; g.ldc = D_LLM; g.resid = xin; g.ldr = D_LLM;
-    if (e->stat_fuse) g.stat_out = e->l_stats;
+    if (sm != STATS_KERNEL) g.stat_out = e->l_stats;
     CK(vla::gemm_launch(g, s, &_err));
     g = vla::GemmArgs();
-    if (e->fold_norms && e->stat_fuse) {
+    if (e->fold_norms && sm != STATS_KERNEL) {
       g.A = xout; g.stat_in = e->l_stats; g.stat_dim = D_LLM; g.stat_eps = LLM_EPS; g.stat_rms = 1;
     } else if (e->fold_norms) {
       CK(vla::row_stats_launch(xout, M, D_LLM, D_LLM, 1, LLM_EPS, e->l_stats, s, &_err));
@@ -589,7 +605,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     g = vla::GemmArgs();
     g.A = e->l_act; g.lda = I_LLM; g.rows = M; g.W = w.wdown; g.ldw = I_LLM; g.N = D_LLM; g.K = I_LLM;
     g.C = xout; g.ldc = D_LLM; g.resid = xout; g.ldr = D_LLM;
-    if (e->stat_fuse && l + 1 < NL) g.stat_out = e->l_stats;
+    if (sm != STATS_KERNEL && l + 1 < NL) g.stat_out = e->l_stats;
     CK(vla::gemm_launch(g, s, &_err));
     if (small && l + 1 < NL) {  // hid[l+1] is final: its policy K|V projections start now, beside the next LLM layer
       rc = policy_kv_from_llm(e, l, e->hid[l + 1], B, L, prompt_len, s, s2);

@@ -881,8 +881,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream, const char** err) {
   }();
   const bool can_stage = a.resid && !pack && !swiglu && a.rope_cols == 0 && (a.batches == 1 || a.r_batch_stride != 0);
   const bool staged = can_stage && (a.resid_staged < 0 ? (staged_env != 0 || a.stat_out != nullptr) : a.resid_staged != 0);
-  if (a.stat_out && a.resid && !staged) {
-    if (err) *err = "gemm: stat_out with a residual needs the staged-residual epilogue";
+  if (a.stat_out && a.resid && !staged && (in_place || a.batches != 1)) {
+    // (out of place, the plain epilogue reads the residual rows itself and sees the final values too)
+    if (err) *err = "gemm: stat_out with an in-place residual needs the staged-residual epilogue";
     return -1;
   }
   if (a.stat_out && 2 * ((a.N + bn - 1) / bn) > STAT_SLOTS) {
