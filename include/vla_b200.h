@@ -131,6 +131,19 @@ int vla_predict_host_u8(vla_engine* e, const uint8_t* images, const int64_t* ext
  * vla_finalize. */
 int vla_set_image_norm(vla_engine* e, const float* mean, const float* stdv);
 
+/* Device-side centre crop for the uint8 entry points: with crop_scale > 0 (the reference uses 0.9,
+ * experiments/robot/openvla_utils.py:616-648 `center_crop_image` -> :568-613 `crop_and_resize`) every 224 x 224 frame
+ * handed to vla_predict_u8 / vla_predict_host_u8 is first replaced by the centred box of that relative AREA, resampled
+ * bilinearly to 224 x 224 with TensorFlow's crop_and_resize arithmetic and converted back to uint8 like
+ * tf.image.convert_image_dtype - bit-exact against the CPU restatement oracle/image_prep.py (TensorFlow itself is not
+ * available offline: that restatement is unpinned).  0 switches it off.  After vla_finalize.  What stays on the CPU
+ * is the first half of the reference's preparation: the JPEG round trip and the lanczos3 antialiased resize from the
+ * camera resolution (:560-565), which depend on TensorFlow's JPEG codec.
+ * vla_op_center_crop_u8 is the kernel alone: (n, H, W, 3) uint8 -> (n, out, out, 3) uint8, device pointers. */
+int vla_set_center_crop(vla_engine* e, float crop_scale);
+int vla_op_center_crop_u8(const uint8_t* in, uint8_t* out, long long n_images, int H, int W, int out_size,
+                          float crop_scale, void* stream);
+
 /* Per-subsystem timing of the forward, for bench.py: with vla_segment_timing(e, 1) the next calls run eagerly (no
  * graph replay) with CUDA events at the subsystem boundaries; vla_segment_times returns the device time [ms] of the
  * last call's (0) vision towers + projector, (1) LLM input assembly + Qwen2.5 prefill, (2) Bridge-Attention policy. */

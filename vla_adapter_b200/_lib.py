@@ -46,6 +46,8 @@ SIGNATURES = {
                                c_void_p, c_void_p]),
     "vla_predict_host_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
+    "vla_set_center_crop": (c_int, [c_void_p, c_float]),
+    "vla_op_center_crop_u8": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_float, c_void_p]),
     "vla_set_image_norm": (c_int, [c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vla_segment_timing": (c_int, [c_void_p, c_int]),
     "vla_segment_times": (c_int, [c_void_p, C.POINTER(C.c_float)]),

@@ -121,6 +121,13 @@ int vla_op_block_tail(const void* a, int lda, int rows, const void* W1, int ldw1
   return rc ? fail(rc, err) : 0;
 }
 
+int vla_op_center_crop_u8(const uint8_t* in, uint8_t* out, long long n_images, int H, int W, int out_size,
+                          float crop_scale, void* stream) {
+  const char* err = nullptr;
+  int rc = vla::center_crop_u8_launch(in, out, n_images, H, W, out_size, crop_scale, static_cast<cudaStream_t>(stream), &err);
+  return rc ? fail(rc, err) : 0;
+}
+
 int vla_op_rmsnorm(const void* x, int rows, int dim, int ldx, const float* w, float eps, void* y, int ldy,
                    void* stream) {
   const char* err = nullptr;

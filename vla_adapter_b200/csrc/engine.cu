@@ -126,6 +126,8 @@ struct vla_engine {
   float *head_ln2w, *head_ln2b, *head_fc2_b, *pp_b1, *pp_b2;
   float *prope_cos = nullptr, *prope_sin = nullptr;
   bf16* img_lut = nullptr;  // [2 towers][3 channels][256]: ToTensor + Normalize + bf16 of a uint8 pixel
+  float crop_scale = 0.f;   // > 0: uint8 frames are centre-cropped on the device first (vla_set_center_crop)
+  uint8_t* crop_buf = nullptr;
   float *st_hi = nullptr, *st_lo = nullptr;
   uint8_t* st_mask = nullptr;
   bool stats_set = false;
@@ -514,6 +516,11 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
 
   const bool seg = e->seg_on && e->seg_ev[0];  // graph capture is off while segment timing is on
   if (seg) cudaEventRecord(e->seg_ev[0], s);
+  if (pix_u8 && e->crop_scale > 0.f) {  // center_crop_image (OU:616-648) on the device, in front of the patch gather
+    CK(vla::center_crop_u8_launch(pix_u8, e->crop_buf, static_cast<long long>(B) * e->cfg.n_images, 224, 224, 224,
+                                  e->crop_scale, s, &_err));
+    pix_u8 = e->crop_buf;
+  }
   // Small batches leave most SMs idle inside every kernel: independent work goes to a side stream (the fork / join
   // are events, so inside a captured CUDA graph they become parallel branches).
   const bool small = e->small_B > 0 && B <= e->small_B;
@@ -1122,6 +1129,28 @@ int vla_predict_u8(vla_engine* e, const uint8_t* images, const int64_t* ext_ids,
                    const int32_t* prompt_len, const float* proprio, int B, int L, float* out_norm, float* out_unnorm,
                    void* out_last_ha, void* stream) {
   return predict_impl(e, images, 1, ext_ids, aq_index, proprio, prompt_len, B, L, out_norm, out_unnorm, out_last_ha, stream);
+}
+
+int vla_set_center_crop(vla_engine* e, float crop_scale) {
+  if (!e) return VLA_ERR_INVALID;
+  if (crop_scale < 0.f || crop_scale > 1.f) return e->fail(VLA_ERR_INVALID, "set_center_crop: crop_scale outside [0, 1]");
+  if (!e->finalized) return e->fail(VLA_ERR_NOT_FINALIZED, "vla_set_center_crop before vla_finalize");
+  vla::DeviceGuard guard(e->device);
+  if (crop_scale > 0.f && !e->crop_buf) {
+    try {
+      e->crop_buf = e->dalloc<uint8_t>(static_cast<size_t>(e->maxB) * e->cfg.n_images * 224 * 224 * 3);
+    } catch (const std::exception& ex) {
+      return e->fail(VLA_ERR_CUDA, ex.what());
+    }
+  }
+  if (crop_scale != e->crop_scale) {  // captured graphs hold the old choice
+    cudaDeviceSynchronize();
+    for (auto& g : e->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    e->graphs.clear();
+  }
+  e->crop_scale = crop_scale;
+  return VLA_OK;
 }
 
 int vla_set_image_norm(vla_engine* e, const float* mean, const float* stdv) {

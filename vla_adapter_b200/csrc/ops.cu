@@ -316,6 +316,46 @@ im2col_u8_kernel(const uint8_t* __restrict__ img, int n_img, int tower, long lon
   for (int i = 0; i < 14; ++i) dst[i] = t[__ldg(src + i * 3)];
 }
 
+// ------------------------------------------------------------------ centre crop (device-side image front-end)
+// center_crop_image of the reference (experiments/robot/openvla_utils.py:616-648 -> crop_and_resize :568-613): the
+// centred box of relative side sqrt(crop_scale), resampled bilinearly to out x out with TensorFlow's crop_and_resize
+// arithmetic, uint8 -> [0,1] float -> uint8 (x 255.5, truncated).  Every product and sum is rounded separately
+// (__fmul_rn / __fadd_rn: no FMA contraction), in the order of oracle/image_prep.py, so the two agree bit for bit.
+__global__ void __launch_bounds__(256)
+center_crop_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long n_images, int H, int W,
+                      int osz, float y0, float x0, float hs, float ws) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_images * osz * osz) return;
+  const int ox = static_cast<int>(idx % osz);
+  const int oy = static_cast<int>((idx / osz) % osz);
+  const long long im = idx / (static_cast<long long>(osz) * osz);
+  const float in_y = __fadd_rn(y0, __fmul_rn(static_cast<float>(oy), hs));
+  const float in_x = __fadd_rn(x0, __fmul_rn(static_cast<float>(ox), ws));
+  const float fy = floorf(in_y), fx = floorf(in_x);
+  const int top = static_cast<int>(fy), bot = static_cast<int>(ceilf(in_y));
+  const int left = static_cast<int>(fx), right = static_cast<int>(ceilf(in_x));
+  const float yl = __fsub_rn(in_y, fy), xl = __fsub_rn(in_x, fx);
+  const uint8_t* base = in + im * H * W * 3LL;
+  const float k = static_cast<float>(1.0 / 255.0);
+  uint8_t* o = out + idx * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float tl = __fmul_rn(static_cast<float>(base[(static_cast<long long>(top) * W + left) * 3 + c]), k);
+    const float tr = __fmul_rn(static_cast<float>(base[(static_cast<long long>(top) * W + right) * 3 + c]), k);
+    const float bl = __fmul_rn(static_cast<float>(base[(static_cast<long long>(bot) * W + left) * 3 + c]), k);
+    const float br = __fmul_rn(static_cast<float>(base[(static_cast<long long>(bot) * W + right) * 3 + c]), k);
+    const float t = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), xl));
+    const float b = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), xl));
+    float v = __fadd_rn(t, __fmul_rn(__fsub_rn(b, t), yl));
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    int q = __float2int_rz(__fmul_rn(v, 255.5f));
+    q = q < 0 ? 0 : (q > 255 ? 255 : q);
+    o[c] = static_cast<uint8_t>(q);
+  }
+}
+
 // ------------------------------------------------------------------ im2col for the 14x14/14 patch conv
 // One thread per (patch row vector of 14 pixels): reads 14 contiguous bf16 (28 B) of the image, writes
 // them at k = c*196 + ky*14 + [0,14).  Grid: (image slab, patch) x (c, ky).
@@ -585,6 +625,29 @@ int im2col_u8_launch(const uint8_t* img, int B, int n_img, int tower, const __nv
   const long long total = n_slabs * 256 * 43;
   launch_kernel(im2col_u8_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, img, n_img, tower, n_slabs,
                 lut, out);
+  return check_launch(err);
+}
+
+int center_crop_u8_launch(const uint8_t* in, uint8_t* out, long long n_images, int H, int W, int out_size,
+                          float crop_scale, cudaStream_t s, const char** err) {
+  if (n_images <= 0 || H < 2 || W < 2 || out_size < 2 || !(crop_scale > 0.f) || crop_scale > 1.f) {
+    if (err) *err = "center_crop: bad shape or crop_scale outside (0, 1]";
+    return -1;
+  }
+  // the box of openvla_utils.py:588-603, every operation rounded to fp32 in the order of oracle/image_prep.py
+  volatile float side = sqrtf(crop_scale);
+  if (side > 1.f) side = 1.f;
+  volatile float off = (1.f - side) / 2.f;
+  volatile float y2 = off + side;
+  volatile float dh = (y2 - off) * static_cast<float>(H - 1);
+  volatile float hs = dh / static_cast<float>(out_size - 1);
+  volatile float dw = (y2 - off) * static_cast<float>(W - 1);
+  volatile float ws = dw / static_cast<float>(out_size - 1);
+  volatile float y0 = off * static_cast<float>(H - 1);
+  volatile float x0 = off * static_cast<float>(W - 1);
+  const long long total = n_images * out_size * out_size;
+  launch_kernel(center_crop_u8_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, in, out, n_images, H, W,
+                out_size, static_cast<float>(y0), static_cast<float>(x0), static_cast<float>(hs), static_cast<float>(ws));
   return check_launch(err);
 }
 

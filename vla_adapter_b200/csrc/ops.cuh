@@ -70,6 +70,12 @@ int im2col_launch(const __nv_bfloat16* pix, int B, int n_img, int tower, __nv_bf
 int im2col_u8_launch(const uint8_t* img, int B, int n_img, int tower, const __nv_bfloat16* lut, __nv_bfloat16* out,
                      cudaStream_t s, const char** err);
 
+// The reference's centre crop (openvla_utils.py:616-648): (n, H, W, 3) uint8 -> (n, out, out, 3) uint8, the centred box of
+// area `crop_scale` resampled bilinearly with TensorFlow's crop_and_resize arithmetic (bit-exact against
+// oracle/image_prep.py).
+int center_crop_u8_launch(const uint8_t* in, uint8_t* out, long long n_images, int H, int W, int out_size,
+                          float crop_scale, cudaStream_t s, const char** err);
+
 // Writes the DINOv2 prefix rows (cls + 4 register tokens, no pos-embed) of every image slab.
 int prefix_tokens_launch(__nv_bfloat16* x, int n_slabs, long long slab_stride, int dim,
                          const __nv_bfloat16* prefix /*[5, dim]*/, int n_prefix, cudaStream_t s,

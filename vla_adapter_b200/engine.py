@@ -302,6 +302,11 @@ class VLAEngine:
         sd = (C.c_float * 6)(*[float(v) for row in std for v in row])
         _lib.check(self.lib.vla_set_image_norm(self._h, m, sd), self._h)
 
+    def set_center_crop(self, crop_scale: float = 0.9) -> None:
+        """uint8 frames are centre-cropped on the device (the reference's center_crop_image, OU:616-648) before the
+        patch gather; 0 switches it off.  Applies to predict_host_u8 / predict_action_batch(images_u8=...)."""
+        _lib.check(self.lib.vla_set_center_crop(self._h, float(crop_scale)), self._h)
+
     def predict_action_batch(self, input_ids, attention_mask=None, pixel_values=None, proprio=None,
                              unnorm_key=None, return_hidden: bool = False, images_u8=None):
         """(B, L) ids + (B, 6n, 224, 224) pixels + (B, P) proprio -> un-normalised actions (B, T, A) float64

@@ -120,6 +120,16 @@ def block_tail(a, W1, bias1, colscale1, x, norm_w, norm_b, W2, bias2, eps=1e-6, 
     return out, partials
 
 
+def center_crop_u8(images: torch.Tensor, crop_scale: float = 0.9, out_size: int = 224) -> torch.Tensor:
+    """(n, H, W, 3) uint8 CUDA -> (n, out, out, 3) uint8: the reference's centre crop (openvla_utils.py:616-648)."""
+    _need_cuda(images)
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3 and images.is_contiguous()
+    n, H, W, _ = images.shape
+    out = torch.empty((n, out_size, out_size, 3), dtype=torch.uint8, device=images.device)
+    _lib.check(_lib.load().vla_op_center_crop_u8(_ptr(images), _ptr(out), n, H, W, out_size, float(crop_scale), _stream()))
+    return out
+
+
 def attention(qkv, B, S, n_heads, n_kv_heads, hd, causal):
     """qkv: (B*S, (n_heads + 2*n_kv_heads) * hd) packed [q | k | v]."""
     _need_cuda(qkv)
