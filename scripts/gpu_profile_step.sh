@@ -6,10 +6,10 @@
 # CUDA-graph replay is switched off (VLA_NO_GRAPH=1) so that ncu's -s/-c launch counting sees plain launches.
 mkdir -p gpurun_out
 export VLA_NO_GRAPH=1
-CMD="timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --latency-iters 0"
+CMD="timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --latency-iters 0"
 rm -f gpurun_out/gemm_shapes.csv
 VLA_GEMM_PROF_CSV=gpurun_out/gemm_shapes.csv $CMD > gpurun_out/plain.log 2>&1 || { tail -5 gpurun_out/plain.log; exit 1; }
-N=$(python -c "import json;print(json.loads(open('gpurun_out/plain.log').read().strip().splitlines()[-1])['gpu_launches'])")
+N=$(python -c "import json;print(json.loads([l for l in open('gpurun_out/plain.log') if l.startswith('{')][-1])['gpu_launches'])")
 echo "launches per step: $N"
 KRE='gemm_bf16|flash_attn|splitkv_attn|fa_tcgen05|norm_kernel|row_stats|rope_apply|im2col|prefix_tokens|assemble|skinny|policy_|head_out|broadcast_row|gather_rows|copy_view'
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \

@@ -17,7 +17,9 @@ def test_restatement_properties():
         assert np.unique(IP.center_crop_image(np.full((224, 224, 3), v, np.uint8))).tolist() == [v]
     out = IP.center_crop_image(img)
     assert out.shape == (224, 224, 3) and out.dtype == np.uint8
-    assert np.array_equal(IP.center_crop_image(img[::-1, ::-1].copy())[::-1, ::-1], out)   # centred: flip-symmetric
+    flipped = IP.center_crop_image(img[::-1, ::-1].copy())[::-1, ::-1]                     # centred: flip-symmetric,
+    d = np.abs(flipped.astype(int) - out.astype(int))                                      # up to fp32 rounding of the
+    assert d.max() <= 1 and (d == 0).mean() > 0.99                                         # sample positions
     y1, x1, y2, x2 = IP.crop_box(0.9)
     assert abs(float((y2 - y1) * (x2 - x1)) - 0.9) < 1e-6 and abs(float(y1 + y2) - 1.0) < 1e-6   # area 0.9, centred
     # a linear ramp is reproduced by bilinear sampling: output pixel i sits at y1*223 + i*(y2-y1)
