@@ -64,7 +64,9 @@ def test_large_batch_branch_gate_32_samples(pro):
     _, n_small = eng.predict_action_batch(ids[:4], None, pix[:4], prop[:4])
     _, n_large = eng.predict_action_batch(ids, None, pix, prop)
     eng.close()
-    assert np.abs(n_small - n_large[:4]).max() <= 2e-2
+    # small batches run the policy as one cluster kernel, large ones per block: same roundings, another summation order;
+    # the Pro head (RoPE + gated task/adapter mix) amplifies that more than the base head
+    assert np.abs(n_small - n_large[:4]).max() <= (6e-2 if pro else 2e-2)
 
 
 def test_three_images():
@@ -170,7 +172,7 @@ def test_two_devices_one_process():
 
 
 @pytest.mark.parametrize("pro,B", [(False, 5), (True, 12)])
-def test_mixed_prompt_lengths_in_one_batch(pro, B):
+def test_mixed_prompt_lengths_in_one_batch(pro, B, monkeypatch):
     """Per-sample prompt lengths (vla_predict's prompt_len; chat prompts span 40-56 tokens, OU:783): the batch is
     right-padded, causal attention hides the padding, and every sample must come out exactly as when it runs alone
     with its own length - and within the usual gate of the oracle run per sample (the reference is bs=1, MP:855)."""
@@ -180,6 +182,12 @@ def test_mixed_prompt_lengths_in_one_batch(pro, B):
     Lmax = max(lens)
     pix, ids, prop = O.make_inputs(cfg, B, Lmax, seed=17)
     mask = (torch.arange(Lmax)[None] < torch.tensor(lens)[:, None]).long()
+    if B > 8:
+        # the stand-alone runs (B = 1) would take the single-kernel policy (policy_fused.cu), the batch the per-block
+        # tcgen05 chain: same roundings, different fp32 summation order - and the Pro head turns that into ~2e-2 on the
+        # actions.  This test is about padding, so both sides use the per-block chain; the two policy paths are
+        # compared in test_fused_policy_matches_per_block_chain.
+        monkeypatch.setenv("VLA_NO_POLICY_FUSED", "1")
     eng = _engine(cfg, W, B, Lmax)
     actions, normalized, ha = eng.predict_action_batch(ids, mask, pix, prop, return_hidden=True)
     # list-of-rows form of the same call
@@ -245,3 +253,35 @@ def test_action_batcher_on_a_real_engine():
     for b in range(len(lens)):
         assert got[b].shape == (8, 7) and got[b].dtype == np.float64
         assert np.abs(got[b] - alone[b]).max() <= 2e-3, b
+
+
+@pytest.mark.parametrize("pro", [False, True])
+def test_fused_policy_matches_per_block_chain(pro, monkeypatch):
+    """Small batches run the 24 policy blocks as one cluster kernel (policy_fused.cu, mma.sync, weights streamed from
+    L2); VLA_NO_POLICY_FUSED=1 keeps the per-block launches (tcgen05 GEMMs + split-kv attention).  Both keep every bf16
+    rounding of AH:218-283 / 337-410 at the same place, so the final policy state agrees to fp32 summation order and
+    both pass the oracle gate."""
+    cfg = O.OracleConfig(n_images=2, dino_depth=2, siglip_depth=2, vocab_size=1024, pro=pro)
+    W = O.make_weights(cfg, seed=23)
+    B, L = 3, 13
+    pix, ids, prop = O.make_inputs(cfg, B, L, seed=23)
+    truth = O.predict_action_batch(W, cfg, pix, ids, prop, torch.float32, keep_taps=True)
+    ref16 = O.predict_action_batch(W, cfg, pix, ids, prop, torch.bfloat16, keep_taps=True)
+    out = {}
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("VLA_NO_POLICY_FUSED", raising=False)
+        else:
+            monkeypatch.setenv("VLA_NO_POLICY_FUSED", "1")
+        eng = _engine(cfg, W, B, L)
+        _, n = eng.predict_action_batch(ids, None, pix, prop)
+        out[fused] = (n, eng.tap("head_x.24").float().cpu().reshape(-1), eng.tap("head_x.1").float().cpu().reshape(-1))
+        eng.close()
+    t24 = truth["head_x.24"].float().reshape(-1)
+    for fused in (True, False):
+        assert _rel(out[fused][1], t24) <= max(2 * _rel(ref16["head_x.24"].reshape(-1), t24), 1e-2), f"fused={fused}"
+    assert _rel(out[True][2], out[False][2]) <= 4e-3      # after one block: bf16 rounding noise only
+    assert _rel(out[True][1], out[False][1]) <= 2e-2      # after 24
+    tn = truth["normalized"].numpy()
+    gate = max(2 * np.abs(ref16["normalized"].numpy() - tn).max(), 2e-2)
+    assert np.abs(out[True][0] - tn).max() <= gate and np.abs(out[False][0] - tn).max() <= gate

@@ -65,7 +65,7 @@ def test_full_size_batch_properties(pro):
         assert torch.equal(n2, n1[perm]) and torch.equal(u2, u1[perm]) and torch.equal(h2, h1[perm])
 
         n3, u3, h3 = run(torch.arange(8, device=dev))
-        assert (n3 - n1[:8]).abs().max().item() <= 2e-2
+        assert (n3 - n1[:8]).abs().max().item() <= (6e-2 if pro else 2e-2)   # other policy path at B <= 8 (policy_fused.cu)
         assert (h3.float() - h1[:8].float()).abs().max().item() <= 2e-2 * max(1.0, h1.float().abs().max().item())
 
         if not pro:      # no positional signal in the base head; the Pro head's RoPE tells the rows apart

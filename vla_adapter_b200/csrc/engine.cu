@@ -10,6 +10,7 @@
 #include "gemm.cuh"
 #include "launch.cuh"
 #include "ops.cuh"
+#include "policy_fused.cuh"
 #include "watchdog.cuh"
 
 #include <cmath>
@@ -154,6 +155,11 @@ struct vla_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_layer, ev_kv;
   std::vector<bf16*> head_x;  // 25 policy states
+  // small-batch mode: the 24 policy blocks run as ONE cluster kernel (policy_fused.cu); per-block pointers on the device
+  std::vector<vla::PolicyBlockW> pol_blocks;
+  int* pol_progress = nullptr;
+  long long* pol_prof = nullptr;  // VLA_POLICY_PROF=1: phase stamps of the fused policy kernel (printed by vla_destroy)
+  int policy_fused = 1;  // VLA_NO_POLICY_FUSED=1 keeps the per-block launches
   int* err_flag = nullptr;
   // pinned/dev staging for vla_predict_host
   void *pin_pix = nullptr, *pin_ids = nullptr, *pin_aq = nullptr, *pin_prop = nullptr, *pin_out = nullptr,
@@ -491,11 +497,16 @@ int policy_kv_gemms(vla_engine* e, int i, const bf16* hs, int B, int L, const in
 // Small-batch mode: the same projections on the side stream, ordered after LLM layer i by an event on the main stream
 // and announced to the policy loop by ev_kv[i].
 int policy_kv_from_llm(vla_engine* e, int i, const bf16* hs, int B, int L, const int32_t* prompt_len, cudaStream_t s,
-                       cudaStream_t s2) {
+                       cudaStream_t s2, bool fused_pro) {
   if (cudaEventRecord(e->ev_layer[i], s) != cudaSuccess || cudaStreamWaitEvent(s2, e->ev_layer[i], 0) != cudaSuccess)
     return e->fail(VLA_ERR_CUDA, "policy K|V fork failed");
   const int rc = policy_kv_gemms(e, i, hs, B, L, prompt_len, e->h_kv_blk[i], s2);
   if (rc) return rc;
+  if (fused_pro) {  // the fused policy kernel rotates q and the self keys itself; these rows are rotated here, once
+    const char* _err = nullptr;
+    const int rr = vla::policy_rope_launch(nullptr, e->h_kv_blk[i], B, e->T, e->NP, e->prope_cos, e->prope_sin, s2, &_err, 1);
+    if (rr) return e->fail(rr, _err ? _err : "policy rope failed");
+  }
   if (cudaEventRecord(e->ev_kv[i], s2) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V event failed");
   return 0;
 }
@@ -527,9 +538,27 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
   cudaStream_t s2 = small ? e->side : s;
 
   // ---------------- vision towers + projector (MP:196-237, 261-273)
+  const bool pro = e->cfg.variant == VLA_HEAD_PRO;
+  const int NK = T + N_AQ + 1 + NP;  // policy keys per sample: self | h_a ++ p | h_t
+  const long long kv_bs = static_cast<long long>(NK) * PKV;
+  // Small batches with a chunk of at most 16 rows: the 24 policy blocks are ONE cluster kernel (policy_fused.cu).
+  const bool fused = small && e->policy_fused && !e->pol_blocks.empty() && e->pol_blocks.size() <= vla::POLICY_FUSED_MAX_BLOCKS && T <= 16;
   if (small) {
     if (cudaEventRecord(e->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(s2, e->ev_fork, 0) != cudaSuccess)
       return e->fail(VLA_ERR_CUDA, "side stream fork failed");
+  }
+  if (fused) {
+    // everything of the policy that depends on the proprio vector only runs first, on the side stream: the projector
+    // (PJ:19-24), the proprio row's K|V for all 24 blocks, and its copy into every block's key/value buffer (row T+64)
+    CK(vla::skinny_linear_launch(proprio, 1, P, B, P, e->pp_w1, P, D_LLM, e->pp_b1, 1, e->h_p1, D_LLM, nullptr, s2, &_err));
+    CK(vla::skinny_linear_launch(e->h_p1, 0, D_LLM, B, D_LLM, e->pp_w2, D_LLM, D_LLM, e->pp_b2, 0, e->h_p, D_LLM, nullptr, s2, &_err));
+    vla::GemmArgs g;
+    g.A = e->h_p; g.lda = D_LLM; g.rows = B; g.W = e->wkv_cond_all; g.ldw = D_LLM; g.N = 24 * PKV; g.K = D_LLM;
+    g.C = e->h_pkv; g.ldc = 24 * PKV; g.bias = e->bkv_cond_all;
+    CK(vla::gemm_launch(g, s2, &_err));
+    for (int i = 0; i < 24; ++i)
+      CK(vla::copy_view_launch(e->h_pkv + static_cast<long long>(i) * PKV, 24LL * PKV, PKV,
+                               e->h_kv_blk[i] + static_cast<long long>(T + N_AQ) * PKV, kv_bs, PKV, 1, B, PKV, s2, &_err));
   }
   int rc = run_tower(e, e->dino, pix, pix_u8, B, 0, s2);  // the shorter tower rides on the side stream
   if (rc) return rc;
@@ -615,22 +644,35 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     if (sm != STATS_KERNEL && l + 1 < NL) g.stat_out = e->l_stats;
     CK(vla::gemm_launch(g, s, &_err));
     if (small && l + 1 < NL) {  // hid[l+1] is final: its policy K|V projections start now, beside the next LLM layer
-      rc = policy_kv_from_llm(e, l, e->hid[l + 1], B, L, prompt_len, s, s2);
+      rc = policy_kv_from_llm(e, l, e->hid[l + 1], B, L, prompt_len, s, s2, fused && pro);
       if (rc) return rc;
     }
   }
   // hidden_states[-1] is the post-final-norm state (HF output_hidden_states semantics)
   CK(vla::rmsnorm_launch(e->l_tmp, M, D_LLM, D_LLM, e->llm_norm, LLM_EPS, e->hid[NL], D_LLM, s, &_err));
   if (small) {
-    rc = policy_kv_from_llm(e, NL - 1, e->hid[NL], B, L, prompt_len, s, s2);
+    rc = policy_kv_from_llm(e, NL - 1, e->hid[NL], B, L, prompt_len, s, s2, fused && pro);
     if (rc) return rc;
   }
 
   if (seg) cudaEventRecord(e->seg_ev[2], s);
   // ---------------- Bridge-Attention policy (AH:43-81, 111-121, 218-283 / 337-410)
+  const int NB = static_cast<int>(e->head.size());
+  const int ha_row0 = NP + L - 1;  // MP:855 with NUM_PROMPT_TOKENS = L-1 (MP:927)
+  if (fused) {
+    // every block's cond / vision K|V rows are on their way on the side stream; the last event orders them all
+    if (cudaStreamWaitEvent(s, e->ev_kv[NB - 1], 0) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V join failed");
+    CK(vla::broadcast_row_launch(e->x0, D_LLM, B * T, e->head_x[0], s, &_err));
+    vla::PolicyFusedArgs pa;
+    for (int i = 0; i < NB; ++i) pa.blocks[i] = e->pol_blocks[i];
+    pa.n_blocks = NB; pa.x0 = e->head_x[0]; pa.ao = e->h_ao; pa.y = e->h_y;
+    pa.T = T; pa.NK = NK; pa.pro = pro ? 1 : 0; pa.rope_cos = e->prope_cos; pa.rope_sin = e->prope_sin;
+    pa.scale_log2 = (1.0f / sqrtf(112.0f)) * 1.4426950408889634f; pa.ln_eps = HEAD_EPS;
+    pa.B = B; pa.progress = e->pol_progress; pa.prof = e->pol_prof;
+    CK(vla::policy_fused_launch(pa, B, s, &_err));
+  } else {
   CK(vla::skinny_linear_launch(proprio, 1, P, B, P, e->pp_w1, P, D_LLM, e->pp_b1, 1, e->h_p1, D_LLM, nullptr, s, &_err));
   CK(vla::skinny_linear_launch(e->h_p1, 0, D_LLM, B, D_LLM, e->pp_w2, D_LLM, D_LLM, e->pp_b2, 0, e->h_p, D_LLM, nullptr, s, &_err));
-  const int NB = static_cast<int>(e->head.size());
   {
     vla::GemmArgs g;  // K|V of the proprio row for all 24 blocks at once
     g.A = e->h_p; g.lda = D_LLM; g.rows = B; g.W = e->wkv_cond_all; g.ldw = D_LLM; g.N = 24 * PKV; g.K = D_LLM;
@@ -638,10 +680,6 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     CK(vla::gemm_launch(g, s, &_err));
   }
   CK(vla::broadcast_row_launch(e->x0, D_LLM, B * T, e->head_x[0], s, &_err));
-  const int ha_row0 = NP + L - 1;  // MP:855 with NUM_PROMPT_TOKENS = L-1 (MP:927)
-  const int NK = T + N_AQ + 1 + NP;  // keys per sample: self | h_a ++ p | h_t
-  const long long kv_bs = static_cast<long long>(NK) * PKV;
-  const bool pro = e->cfg.variant == VLA_HEAD_PRO;
   for (int i = 0; i < NB; ++i) {
     const HeadBlock& w = e->head[i];
     const bf16* hs = e->hid[i + 1];  // AH:118: block i reads hidden state i+1
@@ -680,6 +718,7 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     g.C = e->head_x[i + 1]; g.ldc = D_LLM; g.bias = w.bffn; g.act = vla::ACT_RELU;
     CK(vla::gemm_launch(g, s, &_err));
   }
+  }  // !fused
   CK(vla::head_out_launch(e->head_x[NB], B * T, e->head_ln2w, e->head_ln2b, e->head_fc2_w, e->head_fc2_b, A,
                           e->st_hi, e->st_lo, e->st_mask, out_norm, out_unnorm, s, &_err));
   if (seg) cudaEventRecord(e->seg_ev[3], s);
@@ -712,6 +751,7 @@ int vla_create(const vla_cfg* cfg, vla_engine** out) {
   if (const char* ng = getenv("VLA_NO_GRAPH")) e->use_graphs = atoi(ng) ? 0 : 1;
   if (const char* nf = getenv("VLA_NO_NORM_FOLD")) e->fold_norms = atoi(nf) ? 0 : 1;
   if (const char* sf = getenv("VLA_STAT_FUSE")) e->stat_fuse = atoi(sf) ? 1 : 0;
+  if (const char* pf = getenv("VLA_NO_POLICY_FUSED")) e->policy_fused = atoi(pf) ? 0 : 1;
   if (!e->fold_norms) e->stat_fuse = 0;
   const vla_cfg& c = e->cfg;
   if (c.n_images < 1 || c.n_images > 3) return e->fail(VLA_ERR_INVALID, "n_images must be 1..3");
@@ -1020,6 +1060,22 @@ int vla_finalize(vla_engine* e) {
     e->h_y = e->dalloc<bf16>(BT * D_LLM);
     e->h_yn = e->dalloc<bf16>(BT * D_LLM);
     for (int i = 0; i <= 24; ++i) e->head_x.push_back(e->dalloc<bf16>(BT * D_LLM));
+    if (e->small_B) {  // pointer table of the fused small-batch policy kernel
+      std::vector<vla::PolicyBlockW> pb(24);
+      for (int i = 0; i < 24; ++i) {
+        const HeadBlock& w = e->head[i];
+        pb[i].wq = w.wq; pb[i].wkvs = w.wkv_self; pb[i].wo = w.wo; pb[i].wffn = w.wffn;
+        pb[i].bq = w.bq; pb[i].bkvs = w.bkv_self; pb[i].bo = w.bo; pb[i].lnw = w.ffn_lnw; pb[i].lnb = w.ffn_lnb;
+        pb[i].bffn = w.bffn; pb[i].kv = e->h_kv_blk[i]; pb[i].x_out = e->head_x[i + 1];
+      }
+      e->pol_blocks = pb;
+      e->pol_progress = e->dalloc<int>(1);
+      cudaMemset(e->pol_progress, 0, sizeof(int));
+      if (getenv("VLA_POLICY_PROF")) {
+        e->pol_prof = e->dalloc<long long>(24 * 8);
+        cudaMemset(e->pol_prof, 0, 24 * 8 * sizeof(long long));
+      }
+    }
     e->err_flag = e->dalloc<int>(1);
     cudaMemset(e->err_flag, 0, sizeof(int));
     e->rope_cos = e->dalloc<float>(static_cast<size_t>(S) * 32);
@@ -1348,6 +1404,18 @@ void vla_destroy(vla_engine* e) {
   if (!e) return;
   vla::DeviceGuard guard(e->device);
   cudaDeviceSynchronize();
+  if (e->pol_prof) {  // VLA_POLICY_PROF=1: phase stamps (clocks since the block's start) of the last fused policy launch
+    long long h[24 * 8];
+    if (cudaMemcpy(h, e->pol_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "policy_fused phases (clocks): blk  proj  attn  merge+ao  csync  oproj  csync+ln  ffn  csync+reload\n");
+      for (int b = 0; b < 24; ++b) {
+        const long long* t = h + b * 8;
+        const long long next = b + 1 < 24 ? h[(b + 1) * 8] : t[7];
+        fprintf(stderr, "policy_fused %2d  %lld %lld %lld %lld %lld %lld %lld %lld\n", b, t[1] - t[0], t[2] - t[1], t[3] - t[2],
+                t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], next - t[7]);
+      }
+    }
+  }
   for (auto& g : e->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (e->gev_in) cudaEventDestroy(e->gev_in);

@@ -99,8 +99,9 @@ int skinny_linear_launch(const void* x, int x_is_f32, int ldx, int M, int K, con
 // Pro-variant RoPE (action_heads.py:125-164, 381-386), in place: q rows (B*T, ld 896) at positions t, and the K
 // half of the per-sample key/value buffer kv [B][T+65+NP][1792]: self rows at positions 0..T-1, the 65
 // h_a ++ p rows at 0..64, the NP h_t rows at 0..NP-1.
+// kv_only != 0: only the cond / vision key rows [T, T+65+NP) (q may be null).
 int policy_rope_launch(__nv_bfloat16* q, __nv_bfloat16* kv, int B, int T, int NP, const float* cos_t,
-                       const float* sin_t, cudaStream_t s, const char** err);
+                       const float* sin_t, cudaStream_t s, const char** err, int kv_only = 0);
 
 // Final regression epilogue: out_norm[b,t,a] = fc2(LN(x)) ; out_unnorm = where(mask, 0.5*(a+1)*(hi-lo+1e-8)+lo, a)
 int head_out_launch(const __nv_bfloat16* x, int rows, const float* ln_w, const float* ln_b,

@@ -25,17 +25,19 @@ constexpr int PKV = 1792;   // K | V row
 // One thread rotates 8 contiguous lanes (4 pairs) of one head of one row.
 __global__ void __launch_bounds__(256)
 policy_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ kv, int B, int T, int NP,
-                   const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+                   const float* __restrict__ cos_t, const float* __restrict__ sin_t, int kv_only) {
   pdl_wait();  // programmatic dependent launch: predecessors complete, their writes visible
   pdl_launch_dependents();
   const int NK = T + 65 + NP;
-  const int rows_per_b = T + NK;  // q rows then kv rows
+  // kv_only: just the cond / vision key rows [T, NK) (the fused small-batch policy kernel rotates q and the self keys itself)
+  const int skip = kv_only ? 2 * T : 0;
+  const int rows_per_b = T + NK - skip;  // q rows then kv rows
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * rows_per_b * (PD / 8);
   if (idx >= total) return;
   const int chunk = static_cast<int>(idx % (PD / 8));  // 8-lane chunk within the 896-wide row
   const long long t2 = idx / (PD / 8);
-  const int r = static_cast<int>(t2 % rows_per_b);
+  const int r = static_cast<int>(t2 % rows_per_b) + skip;
   const int b = static_cast<int>(t2 / rows_per_b);
   __nv_bfloat16* p;
   int pos;
@@ -170,9 +172,10 @@ inline int finish(const char** err) {
 }  // namespace
 
 int policy_rope_launch(__nv_bfloat16* q, __nv_bfloat16* kv, int B, int T, int NP, const float* cos_t,
-                       const float* sin_t, cudaStream_t s, const char** err) {
-  const long long total = static_cast<long long>(B) * (2 * T + 65 + NP) * (PD / 8);
-  launch_kernel(policy_rope_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, q, kv, B, T, NP, cos_t, sin_t);
+                       const float* sin_t, cudaStream_t s, const char** err, int kv_only) {
+  const long long total = static_cast<long long>(B) * ((kv_only ? 0 : 2 * T) + 65 + NP) * (PD / 8);
+  launch_kernel(policy_rope_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, q, kv, B, T, NP, cos_t, sin_t,
+                kv_only);
   return finish(err);
 }
 
