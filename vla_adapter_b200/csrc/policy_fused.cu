@@ -29,18 +29,19 @@ namespace vla {
 namespace {
 
 constexpr int PF_THREADS = 384;
-constexpr int PF_WARPS = 12;       // bytes in flight per SM bound the weight streaming: 12 warps x 168 registers
+constexpr int PF_WARPS = 12;       // 12 warps x 168 registers (14 warps / deeper unrolls measured slower: the loads then
+                                  // queue at the L1 tag stage - 8 lines per warp load - instead of waiting in registers)
 constexpr int PF_CL = 8;          // CTAs per cluster = attention heads
 constexpr int D = 896, HD = 112, PKV = 1792;
-constexpr int LDA = 928;          // row stride of the A operand in shared memory (bf16): 464 words = 16 banks per row,
-                                  // so the 16-byte fragment loads of rows g and g+1 (one quarter-warp) do not collide
+constexpr int LDA = 904;          // row stride of the A operand in shared memory (bf16): 452 words = 4 banks per row, so
+                                  // the 16-byte fragment loads (32 bytes apart along t) of rows g and g+1 do not collide
 constexpr int LDQ = 120;          // row stride of q_h / staged K, V tiles
 constexpr int SKB = 16;           // keys per step and warp in the attention phase
 constexpr int NT_MAX = 4;         // column tiles (8 wide) one warp carries at once in phase 1 (42 tiles / 12 warps)
 constexpr int NT_OUT = (14 + PF_WARPS - 1) / PF_WARPS;  // ... in phases 3 and 5 (14 tiles)
 constexpr int UNROLL_OUT = 7;
 static_assert(PF_WARPS * NT_MAX >= 42, "phase 1 is a single pass");
-static_assert(PF_WARPS * 16 * (HD + 2) * 4 <= PF_WARPS * 2 * SKB * LDQ * 2, "the merge buffer reuses the K/V tile memory");
+static_assert(PF_WARPS * 16 * (HD + 2) * 4 <= PF_WARPS * 4 * SKB * LDQ * 2, "the merge buffer reuses the K/V tile memory");
 
 VLA_DEVINL void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;
@@ -68,39 +69,49 @@ VLA_DEVINL void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, u
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+VLA_DEVINL void ldg256(const void* p, uint4& lo, uint4& hi) {  // sm_100: 256-bit loads (LDG.E.256), 32-byte aligned
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+
 // acc[i] (16 x 8, rows of A x weight rows n0[i] .. n0[i]+7) = A[16 x 896] W^T for `nt` column tiles of this warp at once.
-// The weight words come straight from global memory (W is [N][896], K contiguous) with ONE 16-byte load per lane, tile
-// and 32-wide k block, UNROLL blocks in flight: the phase is bound by the latency of these loads (one SM streams its
-// share of the block's weights from L2), so bytes in flight are what counts - the first version used 4-byte loads,
-// two k steps in flight, and took ~28 us per phase.  The k index inside a 32-block is permuted the same way for A and
-// B (a sum over k does not care): lane t owns elements [8t, 8t+8) of the block; mma step s takes elements 8t+4s+{0,1}
-// as its "k = 2t, 2t+1" pair and 8t+4s+{2,3} as its "k = 2t+8, 2t+9" pair, which makes both fragments contiguous:
-// the A fragments of a block are one 16-byte shared-memory load per row.
+// The weight words come straight from global memory (W is [N][896], K contiguous) with ONE 32-byte load per lane, tile
+// and 64-wide k block - the four lanes of a row fetch a whole 128-byte line per instruction - and UNROLL blocks in
+// flight: the phase is bound by the load path of the one SM that streams its share of the block's weights from L2
+// (latency, and the L1 tag stage that takes one line per cycle), so bytes per instruction and bytes in flight are what
+// counts.  (History: 4-byte loads, two k steps in flight: ~28 us per phase; 16-byte loads: 9 / 5 us.)  The k index
+// inside a 64-block is permuted the same way for A and B (a sum over k does not care): lane t owns elements
+// [16t, 16t+16) of the block; mma step s = 0..3 takes elements 16t+4s+{0,1} as its "k = 2t, 2t+1" pair and
+// 16t+4s+{2,3} as its "k = 2t+8, 2t+9" pair, which makes both fragments contiguous: the A fragments of a block are
+// two 16-byte shared-memory loads per row.
 template <int NT, int UNROLL>
 VLA_DEVINL void warp_gemm_16xK(const __nv_bfloat16* sA, const __nv_bfloat16* (&wrow)[NT], int nt, int lane,
                                float (&acc)[NT][4]) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  const __nv_bfloat16* a_lo = sA + g * LDA + 8 * t;        // row g
-  const __nv_bfloat16* a_hi = sA + (g + 8) * LDA + 8 * t;  // row g + 8
-  static_assert((D / 32) % UNROLL == 0, "k blocks must divide by the unroll factor");
-  for (int kb = 0; kb < D; kb += 32 * UNROLL) {
-    uint4 wv[UNROLL][NT];
+  const __nv_bfloat16* a_lo = sA + g * LDA + 16 * t;        // row g
+  const __nv_bfloat16* a_hi = sA + (g + 8) * LDA + 16 * t;  // row g + 8
+  static_assert((D / 64) % UNROLL == 0, "k blocks must divide by the unroll factor");
+  for (int kb = 0; kb < D; kb += 64 * UNROLL) {
+    uint4 w0[UNROLL][NT], w1[UNROLL][NT];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
       for (int i = 0; i < NT; ++i)
-        if (i < nt) wv[u][i] = __ldg(reinterpret_cast<const uint4*>(wrow[i] + kb + 32 * u + 8 * t));  // wrow[i]: row n0 + g
+        if (i < nt) ldg256(wrow[i] + kb + 64 * u + 16 * t, w0[u][i], w1[u][i]);  // wrow[i]: row n0 + g
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const uint4 lo = *reinterpret_cast<const uint4*>(a_lo + kb + 32 * u);
-      const uint4 hi = *reinterpret_cast<const uint4*>(a_hi + kb + 32 * u);
+      const uint4 lo0 = *reinterpret_cast<const uint4*>(a_lo + kb + 64 * u), lo1 = *reinterpret_cast<const uint4*>(a_lo + kb + 64 * u + 8);
+      const uint4 hi0 = *reinterpret_cast<const uint4*>(a_hi + kb + 64 * u), hi1 = *reinterpret_cast<const uint4*>(a_hi + kb + 64 * u + 8);
 #pragma unroll
       for (int i = 0; i < NT; ++i) {
         if (i < nt) {
-          mma_bf16(acc[i], lo.x, hi.x, lo.y, hi.y, wv[u][i].x, wv[u][i].y);
-          mma_bf16(acc[i], lo.z, hi.z, lo.w, hi.w, wv[u][i].z, wv[u][i].w);
+          mma_bf16(acc[i], lo0.x, hi0.x, lo0.y, hi0.y, w0[u][i].x, w0[u][i].y);
+          mma_bf16(acc[i], lo0.z, hi0.z, lo0.w, hi0.w, w0[u][i].z, w0[u][i].w);
+          mma_bf16(acc[i], lo1.x, hi1.x, lo1.y, hi1.y, w1[u][i].x, w1[u][i].y);
+          mma_bf16(acc[i], lo1.z, hi1.z, lo1.w, hi1.w, w1[u][i].z, w1[u][i].w);
         }
       }
     }
@@ -164,9 +175,10 @@ __device__ __noinline__ void policy_prefetch_role(const PolicyFusedArgs& a, int 
 __global__ void __cluster_dims__(PF_CL, 1, 1) __launch_bounds__(PF_THREADS, 1)
 policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
   extern __shared__ __align__(16) uint8_t pf_smem[];
-  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(pf_smem);        // [16][LDA]
-  __nv_bfloat16* sQ = sA + 16 * LDA;                                     // [16][LDQ]
-  __nv_bfloat16* sKV = sQ + 16 * LDQ;                                    // per warp [2 stages][K | V][SKB][LDQ]; later the merge buffer
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(pf_smem);        // [16][LDQ]
+  __nv_bfloat16* sA = sQ + 16 * LDQ;                                     // [16][LDA]  (rows >= T are never read back)
+  __nv_bfloat16* sKV = sA;  // per warp [2 stages][K | V][SKB][LDQ], then the merge buffer: the attention phase does not
+                            // need the A operand (phase 3 reloads it), so the two share the memory
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int h = static_cast<int>(cluster_ctarank());                     // this CTA's attention head
   const int b = static_cast<int>(blockIdx.x) / PF_CL;                    // this cluster's sample
@@ -180,8 +192,8 @@ policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
     return;
   }
 
-  // zero the A operand once (rows T..15 must read as zeros), then load x of block 0
-  for (int i = tid; i < 16 * LDA / 8; i += PF_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  // rows T..15 of A and q hold whatever the memory held: an output row of an MMA depends on its own A row only, and
+  // rows >= T of every result are dropped
   for (int i = tid; i < 16 * LDQ / 8; i += PF_THREADS) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   const __nv_bfloat16* x_in = a.x0 + row0 * D;
@@ -212,7 +224,7 @@ policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
         }
       }
       float acc[NT_MAX][4];
-      warp_gemm_16xK<NT_MAX, 4>(sA, wrow, nt, lane, acc);
+      warp_gemm_16xK<NT_MAX, 2>(sA, wrow, nt, lane, acc);
 #pragma unroll
       for (int i = 0; i < NT_MAX; ++i) {
         if (i >= nt) continue;
@@ -246,21 +258,23 @@ policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
     {
       const __nv_bfloat16* gk = kv + h * HD;
       const __nv_bfloat16* gv = kv + D + h * HD;
-      __nv_bfloat16* wK = sKV + warp * (2 * SKB * LDQ);   // one K and one V tile per warp: the 16 warps overlap each other
-      __nv_bfloat16* wV = wK + SKB * LDQ;
+      __nv_bfloat16* wK = sKV + warp * (4 * SKB * LDQ);   // two stages of one K and one V tile per warp
+      __nv_bfloat16* wV = wK + 2 * SKB * LDQ;
       const int per_warp = ((NK + PF_WARPS * SKB - 1) / (PF_WARPS * SKB)) * SKB;
       const int k_begin = warp * per_warp, k_end = min(NK, k_begin + per_warp);
       const int n_it = k_end > k_begin ? (k_end - k_begin + SKB - 1) / SKB : 0;
-      auto load_kv = [&](int it) {
+      auto load_kv = [&](int it, int buf) {
         const int k0 = k_begin + it * SKB;
         for (int i = lane; i < SKB * (HD / 8); i += 32) {
           const int r = i / (HD / 8), c = i % (HD / 8);
           const bool ok = (k0 + r) < k_end;
           const long long off = static_cast<long long>(ok ? k0 + r : 0) * PKV + c * 8;
-          cp_async16(smem_u32(wK + r * LDQ + c * 8), gk + off, ok);
-          cp_async16(smem_u32(wV + r * LDQ + c * 8), gv + off, ok);
+          cp_async16(smem_u32(wK + (buf * SKB + r) * LDQ + c * 8), gk + off, ok);
+          cp_async16(smem_u32(wV + (buf * SKB + r) * LDQ + c * 8), gv + off, ok);
         }
       };
+      if (n_it) load_kv(0, 0);
+      cp_async_commit();
       float o[HD / 8][4];
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
@@ -269,13 +283,14 @@ policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
                                                                                    // 128 registers per thread at 16 warps
       const float sl2 = a.scale_log2;
       for (int it = 0; it < n_it; ++it) {
-        load_kv(it);
+        const int buf = it & 1;
+        if (it + 1 < n_it) load_kv(it + 1, buf ^ 1);
         cp_async_commit();
-        cp_async_wait<0>();
+        cp_async_wait<1>();
         __syncwarp();
         float sc[2][4];
         sc[0][0] = sc[0][1] = sc[0][2] = sc[0][3] = sc[1][0] = sc[1][1] = sc[1][2] = sc[1][3] = 0.f;
-        const __nv_bfloat16* bK = wK;
+        const __nv_bfloat16* bK = wK + buf * SKB * LDQ;
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           uint32_t b0, b1, b2, b3, q0, q1, q2, q3;
@@ -322,7 +337,7 @@ policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
           o[i][0] *= corr[0]; o[i][1] *= corr[0];
           o[i][2] *= corr[1]; o[i][3] *= corr[1];
         }
-        const __nv_bfloat16* bV = wV;
+        const __nv_bfloat16* bV = wV + buf * SKB * LDQ;
 #pragma unroll
         for (int np = 0; np < HD / 16; ++np) {
           uint32_t b0, b1, b2, b3;
@@ -395,7 +410,15 @@ policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
         }
       }
       float acc[NT_OUT][4];
-      warp_gemm_16xK<NT_OUT, UNROLL_OUT>(sA, wrow, nt, lane, acc);
+      if (NT_OUT == 1 || nt == 2) {
+        warp_gemm_16xK<NT_OUT, UNROLL_OUT>(sA, wrow, nt, lane, acc);
+      } else {  // one tile: its own instantiation keeps the 14 loads of the two-tile warps out of this warp's registers
+        const __nv_bfloat16* w1[1] = {wrow[0]};
+        float acc1[1][4];
+        warp_gemm_16xK<1, UNROLL_OUT>(sA, w1, nt, lane, acc1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[0][e] = acc1[0][e];
+      }
 #pragma unroll
       for (int i = 0; i < NT_OUT; ++i) {
         if (i >= nt) continue;
@@ -474,7 +497,15 @@ policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
         }
       }
       float acc[NT_OUT][4];
-      warp_gemm_16xK<NT_OUT, UNROLL_OUT>(sA, wrow, nt, lane, acc);
+      if (NT_OUT == 1 || nt == 2) {
+        warp_gemm_16xK<NT_OUT, UNROLL_OUT>(sA, wrow, nt, lane, acc);
+      } else {  // one tile: its own instantiation keeps the 14 loads of the two-tile warps out of this warp's registers
+        const __nv_bfloat16* w1[1] = {wrow[0]};
+        float acc1[1][4];
+        warp_gemm_16xK<1, UNROLL_OUT>(sA, w1, nt, lane, acc1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[0][e] = acc1[0][e];
+      }
 #pragma unroll
       for (int i = 0; i < NT_OUT; ++i) {
         if (i >= nt) continue;
@@ -501,7 +532,8 @@ policy_fused_kernel(const __grid_constant__ PolicyFusedArgs a) {
 }  // namespace
 
 size_t policy_fused_smem_bytes() {
-  return static_cast<size_t>(16 * LDA + 16 * LDQ + PF_WARPS * 2 * SKB * LDQ) * 2;
+  constexpr size_t a_bytes = 16 * LDA * 2, kv_bytes = static_cast<size_t>(PF_WARPS) * 4 * SKB * LDQ * 2;
+  return 16 * LDQ * 2 + (a_bytes > kv_bytes ? a_bytes : kv_bytes);
 }
 
 int policy_fused_launch(const PolicyFusedArgs& a, int B, cudaStream_t s, const char** err) {
