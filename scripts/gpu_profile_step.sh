@@ -17,6 +17,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 echo "launch list rc=$?"
 tail -2 gpurun_out/plain.log | cut -c1-300
 wc -l gpurun_out/launches.csv gpurun_out/gemm_shapes.csv
+[ -n "$SKIP_FULL" ] && exit 0   # launch list only
 NG=$(wc -l < gpurun_out/gemm_shapes.csv)   # GEMM launches per step
 # full captures: the first LLM gate/up GEMM of the 4th step (148 CTAs = 74 pairs, SwiGLU epilogue) and one attention launch per shape
 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s $((3*NG+203)) -c 1 -f -o gpurun_out/gemm_full $CMD > gpurun_out/ncu_gemm_full.log 2>&1
