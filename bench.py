@@ -31,7 +31,9 @@ import torch  # noqa: E402
 
 _T0 = time.perf_counter()
 _RANK = int(os.environ.get("RANK", "0"))
-STAGE_LIMIT_S = 240  # no single stage of the bench takes longer; a stage that does is a hang
+# no single stage of the bench takes longer than 240 s; a stage that does is a hang (a profiler that replays every
+# kernel needs more: VLA_BENCH_STAGE_LIMIT_S)
+STAGE_LIMIT_S = int(os.environ.get("VLA_BENCH_STAGE_LIMIT_S", "240"))
 
 # stdout carries exactly ONE line, the JSON result.  Anything a library prints to fd 1 (NCCL's banner when NCCL_DEBUG is
 # set, a stray print) goes to stderr for the whole run; the result line is written to the saved descriptor.

@@ -6,7 +6,8 @@
 # CUDA-graph replay is switched off (VLA_NO_GRAPH=1) so that ncu's -s/-c launch counting sees plain launches.
 mkdir -p gpurun_out
 export VLA_NO_GRAPH=1
-CMD="timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --latency-iters 0"
+export VLA_BENCH_STAGE_LIMIT_S=1500   # ncu replays every kernel: a stage takes minutes
+CMD="timeout 900 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --latency-iters 0"
 rm -f gpurun_out/gemm_shapes.csv
 VLA_GEMM_PROF_CSV=gpurun_out/gemm_shapes.csv $CMD > gpurun_out/plain.log 2>&1 || { tail -5 gpurun_out/plain.log; exit 1; }
 N=$(python -c "import json;print(json.loads([l for l in open('gpurun_out/plain.log') if l.startswith('{')][-1])['gpu_launches'])")
