@@ -15,8 +15,9 @@ this image: it is restated from TF's published kernel semantics -
       in_y    = y1 * (H - 1) + y * scale;  top = floor(in_y), bottom = ceil(in_y), lerp = in_y - top   (same in x)
       value   = top_row + (bottom_row - top_row) * y_lerp,   row = left + (right - left) * x_lerp
   convert_image_dtype(float32 -> uint8, saturate=True): saturate_cast(x * 255.5)  (truncation after scaling by max + 0.5)
-PARITY UNPINNED: no TensorFlow here to generate a golden image; the restatement is pinned only by its own properties
-(tests/test_image_prep.py) and the device kernel is bit-exact against it.  After this step the image is already
+PARITY UNPINNED: no TensorFlow here to generate a golden image; the restatement is checked by its own properties and
+against an independent implementation of the same sampling rule (torch grid_sample, align_corners=True: equal to one
+uint8 step, > 99.5 % of pixels exactly; tests/test_image_prep.py), and the device kernel is bit-exact against it.  After this step the image is already
 224 x 224, so the processor's resize / centre-crop (processing_prismatic.py:136-137) are identities and ToTensor +
 Normalize follow (the engine's lookup table, include/vla_b200.h vla_predict_u8).
 The first half of the reference's preparation - JPEG encode / decode and the lanczos3 antialiased resize from the camera

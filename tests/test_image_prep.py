@@ -32,6 +32,29 @@ def test_restatement_properties():
     assert small.shape == (224, 224, 3)
 
 
+@pytest.mark.parametrize("H,W,scale", [(224, 224, 0.9), (200, 240, 0.9), (256, 320, 0.81)])
+def test_restatement_against_an_independent_bilinear_sampler(H, W, scale):
+    """TensorFlow is absent, so the restatement cannot be pinned against tf.image.crop_and_resize itself; the next best
+    thing is an independent implementation of the same sampling rule: torch's grid_sample with align_corners=True puts
+    normalised coordinate c at pixel (c + 1) / 2 * (size - 1), which is crop_and_resize's `y1 * (H - 1) + i * scale`
+    grid when the normalised box corners are mapped linearly.  Different code, different fp32 operation order: the two
+    must agree to one uint8 step, and almost everywhere exactly."""
+    g = np.random.default_rng(5)
+    img = g.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ours = IP.center_crop_image(img, scale)
+    y1, x1, y2, x2 = (float(v) for v in IP.crop_box(scale))
+    n = IP.OPENVLA_IMAGE_SIZE
+    t = torch.linspace(0, 1, n, dtype=torch.float64)
+    ys = (y1 + (y2 - y1) * t) * 2 - 1          # normalised [0,1] box coordinate -> grid_sample's [-1,1]
+    xs = (x1 + (x2 - x1) * t) * 2 - 1
+    grid = torch.stack(torch.meshgrid(ys, xs, indexing="ij")[::-1], -1)[None]    # (1, n, n, 2) as (x, y)
+    x = torch.from_numpy(img).permute(2, 0, 1)[None].double() / 255.0
+    v = torch.nn.functional.grid_sample(x, grid, mode="bilinear", padding_mode="border", align_corners=True)
+    ref = (v.clamp(0, 1) * 255.5).floor().clamp(0, 255)[0].permute(1, 2, 0).numpy().astype(np.int64)
+    d = np.abs(ref - ours.astype(np.int64))
+    assert d.max() <= 1 and (d == 0).mean() > 0.995, (d.max(), (d == 0).mean())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,W,scale", [(224, 224, 0.9), (224, 224, 0.5), (200, 200, 0.9), (256, 320, 0.81)])
 def test_device_crop_is_bit_exact_against_the_restatement(H, W, scale):
