@@ -6,11 +6,12 @@
 // launch latency, not by work: 24 blocks x 8 launches are ~1.2 ms of the 4.9 ms bs=1 forward.  Here one thread-block
 // CLUSTER of 8 CTAs owns one sample and walks all 24 blocks; CTA h owns attention head h (8 heads x 112 = 896):
 //   phase 1  q_h, k_self_h, v_self_h = x W^T + b for head h's 3 x 112 columns (mma.sync m16n8k16, A = the sample's
-//            T <= 16 rows of x in shared memory, B = weight rows streamed from L2), Pro: RoPE on q_h / k_self_h;
-//            q_h stays in shared memory, k|v go to rows [0, T) of the block's key/value buffer
+//            T <= 16 rows of x in shared memory, B = weight rows streamed from L2 with 256-bit loads), Pro: RoPE on
+//            q_h / k_self_h; q_h stays in shared memory, k|v go to rows [0, T) of the block's key/value buffer
 //   phase 2  softmax(q_h K_h^T / sqrt(112)) V_h over the NK = T + 65 + NP keys of the buffer (the cond / vision rows were
-//            projected beforehand by the tcgen05 GEMM on the side stream): the 8 warps split the keys, online softmax
-//            per warp, merge through shared memory (the algorithm of splitkv_attn_kernel in attention.cu)
+//            projected beforehand by the tcgen05 GEMM on the side stream): the 12 warps split the keys, online softmax
+//            per warp over double-buffered cp.async tiles, merge through shared memory (the algorithm of
+//            splitkv_attn_kernel in attention.cu)
 //   -- cluster barrier --   (the 8 heads' outputs are exchanged through global memory / L2)
 //   phase 3  y[:, 112h : 112h+112] = o Wo^T + bo + x          (fp32 add of the residual, one bf16 rounding)
 //   -- cluster barrier --
@@ -19,6 +20,9 @@
 //   -- cluster barrier --   next block
 // Every bf16 rounding of the multi-kernel path is kept at the same place (projection outputs, RoPE products, P before
 // P V, the attention output, y, LN output, x'), so the two paths agree to fp32 summation order.
+// Beside the worker clusters (one per sample) the grid holds PF_PREFETCH_CL clusters of L2 prefetchers (below).
+// Measured (bs=1, profiles/r02_policy_fused_phases.txt): ~30 us per block, 0.77 ms for the 24 blocks against ~1.0 ms for
+// the per-block launches; the weight phases run at the one SM's L2 read rate (~36 B/clk).
 #include "common.cuh"
 #include "launch.cuh"
 #include "ops.cuh"
