@@ -160,6 +160,13 @@ struct vla_engine {
   int* pol_progress = nullptr;
   long long* pol_prof = nullptr;  // VLA_POLICY_PROF=1: phase stamps of the fused policy kernel (printed by vla_destroy)
   int policy_fused = 1;  // VLA_NO_POLICY_FUSED=1 keeps the per-block launches
+  // The fused policy kernel is launched in groups of `policy_group` blocks on its own stream, each as soon as the K|V
+  // rows of its last block are projected: the policy runs BESIDE the LLM prefill and only the last group is left when
+  // the prefill ends.  All dependencies are ordinary stream / graph edges (no kernel ever waits for a later kernel).
+  // VLA_POLICY_GROUP=24 is the single launch after the prefill.
+  int policy_group = 4;
+  cudaStream_t pol = nullptr;
+  cudaEvent_t ev_pol = nullptr;
   int* err_flag = nullptr;
   // pinned/dev staging for vla_predict_host
   void *pin_pix = nullptr, *pin_ids = nullptr, *pin_aq = nullptr, *pin_prop = nullptr, *pin_out = nullptr,
@@ -547,6 +554,27 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     if (cudaEventRecord(e->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(s2, e->ev_fork, 0) != cudaSuccess)
       return e->fail(VLA_ERR_CUDA, "side stream fork failed");
   }
+  const int NB = static_cast<int>(e->head.size());
+  const bool grouped = fused && e->pol && e->policy_group < NB;
+  int pol_next = 0;  // first policy block not launched yet (grouped mode)
+  // one group of the fused policy kernel: blocks [first, last], after the K|V rows of block `last` (and, by stream
+  // order on s2, of every earlier block) are projected
+  auto launch_policy_group = [&](int first, int last, cudaStream_t ps, int prefetch_clusters) -> int {
+    vla::PolicyFusedArgs pa;
+    for (int i = first; i <= last; ++i) pa.blocks[i - first] = e->pol_blocks[i];
+    pa.n_blocks = last - first + 1; pa.x0 = e->head_x[first]; pa.ao = e->h_ao; pa.y = e->h_y;
+    pa.T = T; pa.NK = NK; pa.pro = pro ? 1 : 0; pa.rope_cos = e->prope_cos; pa.rope_sin = e->prope_sin;
+    pa.scale_log2 = (1.0f / sqrtf(112.0f)) * 1.4426950408889634f; pa.ln_eps = HEAD_EPS;
+    pa.B = B; pa.progress = e->pol_progress; pa.prof = first == 0 ? e->pol_prof : nullptr;
+    const char* perr = nullptr;
+    const int prc = vla::policy_fused_launch(pa, B, ps, &perr, prefetch_clusters);
+    if (prc) return e->fail(prc, perr ? perr : "policy_fused launch failed");
+    return 0;
+  };
+  if (grouped) {
+    if (cudaStreamWaitEvent(e->pol, e->ev_fork, 0) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy stream fork failed");
+    CK(vla::broadcast_row_launch(e->x0, D_LLM, B * T, e->head_x[0], e->pol, &_err));
+  }
   if (fused) {
     // everything of the policy that depends on the proprio vector only runs first, on the side stream: the projector
     // (PJ:19-24), the proprio row's K|V for all 24 blocks, and its copy into every block's key/value buffer (row T+64)
@@ -646,6 +674,13 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
     if (small && l + 1 < NL) {  // hid[l+1] is final: its policy K|V projections start now, beside the next LLM layer
       rc = policy_kv_from_llm(e, l, e->hid[l + 1], B, L, prompt_len, s, s2, fused && pro);
       if (rc) return rc;
+      if (grouped && l + 1 - pol_next >= e->policy_group) {
+        vla::PdlScope no_pdl(false);  // a group that started early would hold its SMs idle beside the prefill
+        if (cudaStreamWaitEvent(e->pol, e->ev_kv[l], 0) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V join failed");
+        rc = launch_policy_group(pol_next, l, e->pol, 2);
+        if (rc) return rc;
+        pol_next = l + 1;
+      }
     }
   }
   // hidden_states[-1] is the post-final-norm state (HF output_hidden_states semantics)
@@ -657,19 +692,21 @@ int forward(vla_engine* e, const bf16* pix, const uint8_t* pix_u8, const int64_t
 
   if (seg) cudaEventRecord(e->seg_ev[2], s);
   // ---------------- Bridge-Attention policy (AH:43-81, 111-121, 218-283 / 337-410)
-  const int NB = static_cast<int>(e->head.size());
   const int ha_row0 = NP + L - 1;  // MP:855 with NUM_PROMPT_TOKENS = L-1 (MP:927)
-  if (fused) {
+  if (grouped) {
+    // the last group: nothing else is running any more, so it gets the full set of L2 prefetchers
+    vla::PdlScope no_pdl(false);
+    if (cudaStreamWaitEvent(e->pol, e->ev_kv[NB - 1], 0) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V join failed");
+    rc = launch_policy_group(pol_next, NB - 1, e->pol, -1);
+    if (rc) return rc;
+    if (cudaEventRecord(e->ev_pol, e->pol) != cudaSuccess || cudaStreamWaitEvent(s, e->ev_pol, 0) != cudaSuccess)
+      return e->fail(VLA_ERR_CUDA, "policy stream join failed");
+  } else if (fused) {
     // every block's cond / vision K|V rows are on their way on the side stream; the last event orders them all
     if (cudaStreamWaitEvent(s, e->ev_kv[NB - 1], 0) != cudaSuccess) return e->fail(VLA_ERR_CUDA, "policy K|V join failed");
     CK(vla::broadcast_row_launch(e->x0, D_LLM, B * T, e->head_x[0], s, &_err));
-    vla::PolicyFusedArgs pa;
-    for (int i = 0; i < NB; ++i) pa.blocks[i] = e->pol_blocks[i];
-    pa.n_blocks = NB; pa.x0 = e->head_x[0]; pa.ao = e->h_ao; pa.y = e->h_y;
-    pa.T = T; pa.NK = NK; pa.pro = pro ? 1 : 0; pa.rope_cos = e->prope_cos; pa.rope_sin = e->prope_sin;
-    pa.scale_log2 = (1.0f / sqrtf(112.0f)) * 1.4426950408889634f; pa.ln_eps = HEAD_EPS;
-    pa.B = B; pa.progress = e->pol_progress; pa.prof = e->pol_prof;
-    CK(vla::policy_fused_launch(pa, B, s, &_err));
+    rc = launch_policy_group(0, NB - 1, s, -1);
+    if (rc) return rc;
   } else {
   CK(vla::skinny_linear_launch(proprio, 1, P, B, P, e->pp_w1, P, D_LLM, e->pp_b1, 1, e->h_p1, D_LLM, nullptr, s, &_err));
   CK(vla::skinny_linear_launch(e->h_p1, 0, D_LLM, B, D_LLM, e->pp_w2, D_LLM, D_LLM, e->pp_b2, 0, e->h_p, D_LLM, nullptr, s, &_err));
@@ -752,6 +789,10 @@ int vla_create(const vla_cfg* cfg, vla_engine** out) {
   if (const char* nf = getenv("VLA_NO_NORM_FOLD")) e->fold_norms = atoi(nf) ? 0 : 1;
   if (const char* sf = getenv("VLA_STAT_FUSE")) e->stat_fuse = atoi(sf) ? 1 : 0;
   if (const char* pf = getenv("VLA_NO_POLICY_FUSED")) e->policy_fused = atoi(pf) ? 0 : 1;
+  if (const char* pg = getenv("VLA_POLICY_GROUP")) {
+    const int v = atoi(pg);
+    if (v >= 1) e->policy_group = v;
+  }
   if (!e->fold_norms) e->stat_fuse = 0;
   const vla_cfg& c = e->cfg;
   if (c.n_images < 1 || c.n_images > 3) return e->fail(VLA_ERR_INVALID, "n_images must be 1..3");
@@ -1043,6 +1084,9 @@ int vla_finalize(vla_engine* e) {
         e->h_kv_blk.push_back(e->dalloc<bf16>(static_cast<size_t>(e->small_B) * (e->T + N_AQ + 1 + e->NP) * PKV));
       if (!e->side && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess)
         throw std::runtime_error("side stream creation failed");
+      if (!e->pol && cudaStreamCreateWithFlags(&e->pol, cudaStreamNonBlocking) != cudaSuccess)
+        throw std::runtime_error("policy stream creation failed");
+      if (!e->ev_pol) cudaEventCreateWithFlags(&e->ev_pol, cudaEventDisableTiming);
       if (!e->ev_fork) cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
       if (!e->ev_join) cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
       for (int i = static_cast<int>(e->ev_layer.size()); i < 24; ++i) {
@@ -1428,6 +1472,8 @@ void vla_destroy(vla_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->side) cudaStreamDestroy(e->side);
+  if (e->pol) cudaStreamDestroy(e->pol);
+  if (e->ev_pol) cudaEventDestroy(e->ev_pol);
   for (void* p : e->allocs) cudaFree(p);
   e->free_masters();
   delete e;

@@ -540,7 +540,7 @@ size_t policy_fused_smem_bytes() {
   return 16 * LDQ * 2 + (a_bytes > kv_bytes ? a_bytes : kv_bytes);
 }
 
-int policy_fused_launch(const PolicyFusedArgs& a, int B, cudaStream_t s, const char** err) {
+int policy_fused_launch(const PolicyFusedArgs& a, int B, cudaStream_t s, const char** err, int prefetch_clusters) {
   if (a.T < 1 || a.T > 16 || B < 1 || B != a.B || !a.progress || a.n_blocks < 1 || a.n_blocks > POLICY_FUSED_MAX_BLOCKS) {
     if (err) *err = "policy_fused: chunk length must be 1..16 and the batch positive";
     return -1;
@@ -555,7 +555,8 @@ int policy_fused_launch(const PolicyFusedArgs& a, int B, cudaStream_t s, const c
     }
     attr_set = true;
   }
-  launch_kernel(policy_fused_kernel, dim3((B + PF_PREFETCH_CL) * PF_CL), dim3(PF_THREADS), smem, s, a);
+  const int pf_cl = prefetch_clusters < 0 ? PF_PREFETCH_CL : (prefetch_clusters > PF_PREFETCH_CL ? PF_PREFETCH_CL : prefetch_clusters);
+  launch_kernel(policy_fused_kernel, dim3((B + pf_cl) * PF_CL), dim3(PF_THREADS), smem, s, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = cudaGetErrorString(e);

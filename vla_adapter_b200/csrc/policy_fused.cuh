@@ -33,6 +33,7 @@ struct PolicyFusedArgs {
 
 size_t policy_fused_smem_bytes();
 // One cluster of 8 CTAs per sample (+ 4 clusters of L2 prefetchers): every policy block in one launch.  T <= 16.
-int policy_fused_launch(const PolicyFusedArgs& a, int B, cudaStream_t s, const char** err);
+// prefetch_clusters < 0: the default (4); fewer when the launch shares the GPU with other work.
+int policy_fused_launch(const PolicyFusedArgs& a, int B, cudaStream_t s, const char** err, int prefetch_clusters = -1);
 
 }  // namespace vla
